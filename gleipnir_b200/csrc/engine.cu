@@ -1,0 +1,657 @@
+// The Nested Sampling engine: device-resident outer loop of NestedSampling.run
+// (nested_sampling.py:83-213), k deaths per step.  All run state (counters, prior mass,
+// evidence/information accumulators, proposal widths, batch size) lives in device memory,
+// so a whole run is enqueued without host round trips.
+//
+// Per step:  begin -> select (8 launches, select.cu) -> record -> accumulate
+//            -> walkers (tuning_cycles + 1 launches, walker.cu) -> end_walk
+#include <new>
+#include "engine.cuh"
+#include "philox.cuh"
+
+namespace gl {
+
+// ---- step begin: batch size for this step ------------------------------------------------
+__global__ void begin_kernel(EngineState *S, int k_req, long long n_target, long long N) {
+    long long k = n_target - S->n_dead;
+    if (k > k_req) k = k_req;
+    if (k > N - 1) k = N - 1;          // at least one survivor to seed from
+    if (k < 0) k = 0;
+    S->k_cur = (int)k;
+    S->do_walk = 0;
+}
+
+// ---- record: append the batch to the dead-point log (nested_sampling.py:130-133,170-173) --
+__global__ void __launch_bounds__(256) record_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                     const double *__restrict__ live,
+                                                     const double *__restrict__ logl, int d, long long row_offset,
+                                                     double log_np1, long long capacity, double *__restrict__ dead_x,
+                                                     double *__restrict__ dead_logl, double *__restrict__ dead_w,
+                                                     long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    const int k = S->k_cur;
+    const long long base = S->n_rows;
+    if (k <= 0 || base + k > capacity) return;
+    const double w = exp(S->logX - log_np1);          // X/(N+1): every death of a batch
+    const int step = S->step;
+    const long long total = (long long)k * d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long q = e / d;
+        const int j = (int)(e - q * d);
+        const long long slot = dead_list[q];
+        dead_x[(base + q) * d + j] = live[slot * d + j];
+        if (j == 0) {
+            dead_logl[base + q] = logl[slot];
+            dead_w[base + q] = w;
+            dead_idx[base + q] = slot + row_offset;
+            dead_step[base + q] = step;
+        }
+    }
+}
+
+// ---- accumulate: evidence / information update for the batch (:118-125,160-167) ----------
+__global__ void __launch_bounds__(1024) accumulate_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                          const double *__restrict__ logl, double n_global,
+                                                          long long n_target, long long capacity) {
+    __shared__ double scratch[33];
+    __shared__ unsigned long long kscratch[33];
+    const int k = S->k_cur;
+    if (k <= 0) return;
+    const double logw = S->logX - log(n_global + 1.0);
+    const double w = exp(logw);
+    double mx = -INFINITY;
+    unsigned long long mk = 0ull;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double L = logl[dead_list[i]];
+        const double lw = logw + L;
+        if (isfinite(lw)) mx = fmax(mx, lw);
+        const unsigned long long key = sort_key(L);
+        mk = key > mk ? key : mk;
+    }
+    mx = block_max(mx, scratch);
+    {   // block max of the key -> L*
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        mk = warp_max_u64(mk);
+        __syncthreads();
+        if (lane == 0) kscratch[wid] = mk;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long t = lane < nw ? kscratch[lane] : 0ull;
+            t = warp_max_u64(t);
+            if (lane == 0) kscratch[32] = t;
+        }
+        __syncthreads();
+        mk = kscratch[32];
+    }
+    const double m_old = S->M;
+    const double m_new = fmax(m_old, mx);
+    double sz = 0.0, sh = 0.0, zl = 0.0, hl = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double L = logl[dead_list[i]];
+        const double lw = logw + L;
+        if (isfinite(lw)) {
+            const double t = exp(lw - m_new);
+            sz += t;
+            sh += t * L;
+        }
+        const double dZ = w * exp(L);
+        zl += dZ;
+        const double dH = dZ * L;
+        if (dH == dH) hl += dH;                       // isnan(dH) -> 0  (:122,164)
+    }
+    sz = block_sum(sz, scratch);
+    sh = block_sum(sh, scratch);
+    zl = block_sum(zl, scratch);
+    hl = block_sum(hl, scratch);
+    if (threadIdx.x == 0) {
+        if (mx > -INFINITY) {
+            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+            S->Zs = S->Zs * scale + sz;
+            S->Hs = S->Hs * scale + sh;
+            S->M = m_new;
+        }
+        S->Z_lin += zl;
+        S->H_lin += hl;
+        S->logX += log((n_global - (double)k + 1.0) / (n_global + 1.0));
+        S->n_dead += k;
+        if (S->n_rows + k <= capacity) S->n_rows += k;
+        S->lstar = key_to_double(mk);
+        S->do_walk = S->n_dead < n_target;
+    }
+}
+
+// ---- end of refill: clear the dead flags, persist widths, advance the step ----------------
+__global__ void __launch_bounds__(256) end_walk_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                       unsigned char *is_dead, int d, int tuning_cycles) {
+    const int k = S->k_cur;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
+        is_dead[dead_list[i]] = 0;
+    if (blockIdx.x == 0) {
+        // GL_MAX_DIM <= blockDim: thread j owns component j
+        const int j = threadIdx.x;
+        const double wnew = j < d ? phase_width(S, j, tuning_cycles, k) : 0.0;
+        __syncthreads();          // every width derived before any acc/width is overwritten
+        if (j < d) {
+            S->widths[j] = wnew;
+            for (int c = 0; c < tuning_cycles; ++c) S->acc[c][j] = 0u;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S->step += 1;
+        S->do_walk = 0;
+        S->k_cur = 0;
+    }
+}
+
+// ---- inject: the stub-sampler path of the replay tests ----------------------------------
+// Replacement rows arrive in DEATH order (ascending (logL, index)); dead_list is in index
+// order, so each slot's rank in death order is computed on the fly (k is small in tests).
+__global__ void __launch_bounds__(256) inject_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                     const double *__restrict__ old_logl_by_list,
+                                                     const double *__restrict__ pts, const double *__restrict__ lls,
+                                                     int d, double *__restrict__ live, double *__restrict__ logl) {
+    const int k = S->k_cur;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        const unsigned long long ki = sort_key(old_logl_by_list[i]);
+        int rank = 0;
+        for (int q = 0; q < k; ++q) {
+            const unsigned long long kq = sort_key(old_logl_by_list[q]);
+            rank += (kq < ki) || (kq == ki && q < i);
+        }
+        const long long slot = dead_list[i];
+        for (int j = 0; j < d; ++j) live[slot * d + j] = pts[(size_t)rank * d + j];
+        logl[slot] = lls[rank];
+    }
+}
+__global__ void __launch_bounds__(256) gather_logl_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                          const double *__restrict__ logl, double *__restrict__ out) {
+    const int k = S->k_cur;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
+        out[i] = logl[dead_list[i]];
+}
+
+// ---- initial proposal widths (samplers.py:70-81): 0.5 * range of 100 prior draws ---------
+__global__ void __launch_bounds__(128) init_widths_kernel(EngineState *S, const PriorTable *pt, int d, uint64_t seed) {
+    __shared__ double smin[4], smax[4];
+    const int j = blockIdx.x;
+    if (j >= d) return;
+    double lo = INFINITY, hi = -INFINITY;
+    if (threadIdx.x < 100) {
+        const U2 u = philox_uniforms(seed, (uint32_t)threadIdx.x, 0u, (uint32_t)j, GL_TAG_WIDTH);
+        const double v = prior_ppf(pt->kind[j], pt->p0[j], pt->p1[j], u.a);
+        lo = v;
+        hi = v;
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w) { lo = fmin(lo, smin[w]); hi = fmax(hi, smax[w]); }
+        S->widths[j] = 0.5 * (hi - lo);
+    }
+}
+
+// ---- finalize (nested_sampling.py:183-203) ----------------------------------------------
+struct LsePair {
+    double m, s;
+};
+__device__ __forceinline__ LsePair lse_combine(LsePair a, LsePair b) {
+    if (a.m == -INFINITY) return b;
+    if (b.m == -INFINITY) return a;
+    LsePair r;
+    if (a.m >= b.m) { r.m = a.m; r.s = a.s + b.s * exp(b.m - a.m); }
+    else { r.m = b.m; r.s = b.s + a.s * exp(a.m - b.m); }
+    return r;
+}
+
+constexpr int FIN_THREADS = 256;
+
+// partials[b] = (m, s, linear sum of exp(L), count) over the survivors of block b's chunk
+__global__ void __launch_bounds__(FIN_THREADS) final_partial_kernel(const double *__restrict__ logl,
+                                                                    const unsigned char *__restrict__ is_dead,
+                                                                    long long N, long long chunk, double *partials) {
+    __shared__ double sm_m[FIN_THREADS], sm_s[FIN_THREADS], sm_l[FIN_THREADS], sm_c[FIN_THREADS];
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > N) hi = N;
+    LsePair p{-INFINITY, 0.0};
+    double lin = 0.0, cnt = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += FIN_THREADS) {
+        if (is_dead[i]) continue;
+        const double L = logl[i];
+        cnt += 1.0;
+        lin += exp(L);
+        if (isfinite(L)) p = lse_combine(p, LsePair{L, 1.0});
+    }
+    sm_m[threadIdx.x] = p.m; sm_s[threadIdx.x] = p.s; sm_l[threadIdx.x] = lin; sm_c[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            LsePair a{sm_m[threadIdx.x], sm_s[threadIdx.x]}, b{sm_m[threadIdx.x + o], sm_s[threadIdx.x + o]};
+            a = lse_combine(a, b);
+            sm_m[threadIdx.x] = a.m; sm_s[threadIdx.x] = a.s;
+            sm_l[threadIdx.x] += sm_l[threadIdx.x + o];
+            sm_c[threadIdx.x] += sm_c[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partials[4 * blockIdx.x + 0] = sm_m[0];
+        partials[4 * blockIdx.x + 1] = sm_s[0];
+        partials[4 * blockIdx.x + 2] = sm_l[0];
+        partials[4 * blockIdx.x + 3] = sm_c[0];
+    }
+}
+
+__global__ void final_combine_kernel(EngineState *S, const double *partials, int nblocks) {
+    LsePair p{-INFINITY, 0.0};
+    double lin = 0.0, cnt = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        p = lse_combine(p, LsePair{partials[4 * b], partials[4 * b + 1]});
+        lin += partials[4 * b + 2];
+        cnt += partials[4 * b + 3];
+    }
+    if (cnt <= 0.0) return;
+    const double X = exp(S->logX);
+    const double lm = lin / cnt;                                  // mean likelihood (:187)
+    S->Z_lin += X * lm;
+    const double dH = X * lm * log(lm);
+    if (dH == dH) S->H_lin += dH;
+    if (p.m > -INFINITY) {
+        const double loglm = p.m + log(p.s) - log(cnt);
+        const double lw = S->logX + loglm;
+        const double m_old = S->M, m_new = fmax(m_old, lw);
+        const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+        const double t = exp(lw - m_new);
+        S->Zs = S->Zs * scale + t;
+        S->Hs = S->Hs * scale + t * loglm;
+        S->M = m_new;
+    }
+    S->fin_n = (long long)cnt;
+}
+
+// survivors appended in index order with weight X/(#survivors) (:195-203); a survivor's row
+// position is its index minus the number of dead slots before it (dead_list is ascending).
+__global__ void __launch_bounds__(256) final_rows_kernel(EngineState *S, const long long *__restrict__ dead_list,
+                                                         const unsigned char *__restrict__ is_dead,
+                                                         const double *__restrict__ live,
+                                                         const double *__restrict__ logl, long long N, int d,
+                                                         long long row_offset, long long capacity,
+                                                         double *__restrict__ dead_x, double *__restrict__ dead_logl,
+                                                         double *__restrict__ dead_w, long long *__restrict__ dead_idx,
+                                                         int *__restrict__ dead_step) {
+    const int k = S->k_cur;                      // unreplaced slots of the last batch
+    const long long base = S->n_rows;
+    const long long n_surv = S->fin_n;
+    if (n_surv <= 0 || base + n_surv > capacity) return;
+    const double aw = exp(S->logX) / (double)n_surv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (is_dead[i]) continue;
+        int lo = 0, hi = k;                      // lower_bound(dead_list, i)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (dead_list[mid] < i) lo = mid + 1;
+            else hi = mid;
+        }
+        const long long pos = base + (i - lo);
+        for (int j = 0; j < d; ++j) dead_x[pos * d + j] = live[i * d + j];
+        dead_logl[pos] = logl[i];
+        dead_w[pos] = aw;
+        dead_idx[pos] = i + row_offset;
+        dead_step[pos] = -1;
+    }
+}
+
+__global__ void final_done_kernel(EngineState *S, long long capacity) {
+    if (S->fin_n > 0 && S->n_rows + S->fin_n <= capacity) S->n_rows += S->fin_n;
+    S->finalized = 1;
+}
+
+constexpr int FIN_MAX_BLOCKS = 1024;
+
+}  // namespace gl
+
+// ============================== host side / C ABI ==========================================
+struct gl_ns {
+    gl_ns_config cfg;
+    int d;
+    gl::ModelDev model;
+    const gl_model *model_handle;
+    gl_prior priors[GL_MAX_DIM];
+    gl_ns_buffers buf;
+    // carved out of buf.workspace
+    gl::EngineState *S;
+    gl::SelectState *sel;
+    gl::PriorTable *pt;
+    long long *dead_list;
+    unsigned char *is_dead;
+    double *scratch_x, *scratch_l, *tmp_k, *fin_partials;
+    // host mirrors (deterministic arithmetic; no device reads needed to drive the loop)
+    long long h_n_dead, h_n_evals;
+    int h_step, h_k_last;
+    bool initialized, pending_refill, finalized;
+};
+
+namespace gl {
+
+static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct WorkspaceLayout {
+    size_t off_state, off_sel, off_pt, off_list, off_isdead, off_sx, off_sl, off_tmp, off_fin, total;
+};
+
+static WorkspaceLayout workspace_layout(const gl_ns_config &c, int d) {
+    WorkspaceLayout L;
+    size_t o = 0;
+    const size_t k = (size_t)(c.batch_k > 0 ? c.batch_k : 1);
+    L.off_state = o;  o += align256(sizeof(EngineState));
+    L.off_sel = o;    o += align256(sizeof(SelectState));
+    L.off_pt = o;     o += align256(sizeof(PriorTable));
+    L.off_list = o;   o += align256(sizeof(long long) * k);
+    L.off_isdead = o; o += align256((size_t)c.population_size);
+    L.off_sx = o;     o += align256(sizeof(double) * k * (size_t)d);
+    L.off_sl = o;     o += align256(sizeof(double) * k);
+    L.off_tmp = o;    o += align256(sizeof(double) * k);
+    L.off_fin = o;    o += align256(sizeof(double) * 4 * FIN_MAX_BLOCKS);
+    L.total = o;
+    return L;
+}
+
+static int check_config(const gl_ns_config *cfg, int d) {
+    GL_REQUIRE(cfg != nullptr, "cfg is NULL");
+    GL_REQUIRE(d >= 1 && d <= GL_MAX_DIM, "d=%d outside [1, %d]", d, GL_MAX_DIM);
+    GL_REQUIRE(cfg->population_size >= 2, "population_size must be >= 2");
+    GL_REQUIRE(cfg->batch_k >= 1 && cfg->batch_k < cfg->population_size, "batch_k=%d outside [1, N)", cfg->batch_k);
+    GL_REQUIRE(cfg->iterations >= 0 && cfg->burn_in >= 0, "iterations/burn_in must be >= 0");
+    GL_REQUIRE(cfg->tuning_cycles >= 0 && cfg->tuning_cycles <= GL_MAX_TUNING_CYCLES, "tuning_cycles outside [0, %d]",
+               GL_MAX_TUNING_CYCLES);
+    GL_REQUIRE(cfg->proposal == GL_PROPOSAL_UNIFORM || cfg->proposal == GL_PROPOSAL_NORMAL, "unknown proposal");
+    GL_REQUIRE(cfg->dead_capacity >= 1, "dead_capacity must be >= 1");
+    GL_REQUIRE(cfg->row_offset == 0 && cfg->global_population == cfg->population_size,
+               "sharded engines are driven through the multi-GPU host loop (not yet in this build)");
+    return GL_OK;
+}
+
+static WalkParams walk_params(const gl_ns *ns) {
+    WalkParams P;
+    P.S = ns->S;
+    P.dead_list = ns->dead_list;
+    P.is_dead = ns->is_dead;
+    P.live = ns->buf.live;
+    P.logl = ns->buf.logl;
+    P.priors = ns->pt;
+    P.scratch_x = ns->scratch_x;
+    P.scratch_l = ns->scratch_l;
+    P.N = ns->cfg.population_size;
+    P.row_offset = ns->cfg.row_offset;
+    P.seed = ns->cfg.seed;
+    P.d = ns->d;
+    P.iterations = ns->cfg.iterations;
+    P.burn_in = ns->cfg.burn_in;
+    P.tuning_cycles = ns->cfg.tuning_cycles;
+    P.proposal = ns->cfg.proposal;
+    P.k_max = ns->cfg.batch_k;
+    return P;
+}
+
+static int blocks_for(long long items, int threads, int cap_per_sm) {
+    long long b = (items + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * cap_per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
+    const long long N = ns->cfg.population_size;
+    begin_kernel<<<1, 1, 0, st>>>(ns->S, k_req, n_target, N);
+    int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
+    if (rc) return rc;
+    const double n_global = (double)ns->cfg.global_population;
+    record_kernel<<<blocks_for((long long)k_req * ns->d, 256, 8), 256, 0, st>>>(
+        ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
+        ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
+        ns->buf.dead_step);
+    accumulate_kernel<<<1, 1024, 0, st>>>(ns->S, ns->dead_list, ns->buf.logl, n_global, n_target,
+                                          ns->cfg.dead_capacity);
+    GL_CHECK_LAUNCH();
+    long long k = n_target - ns->h_n_dead;
+    if (k > k_req) k = k_req;
+    if (k > N - 1) k = N - 1;
+    if (k < 0) k = 0;
+    ns->h_k_last = (int)k;
+    ns->h_n_dead += k;
+    ns->pending_refill = k > 0;
+    return GL_OK;
+}
+
+static int end_walk_launch(gl_ns *ns, cudaStream_t st) {
+    end_walk_kernel<<<blocks_for(ns->cfg.batch_k, 256, 4), 256, 0, st>>>(ns->S, ns->dead_list, ns->is_dead, ns->d,
+                                                                          ns->cfg.tuning_cycles);
+    GL_CHECK_LAUNCH();
+    ns->h_step += 1;
+    ns->pending_refill = false;
+    return GL_OK;
+}
+
+static int refill_launch(gl_ns *ns, cudaStream_t st) {
+    int rc = walk_launch(walk_params(ns), ns->model, st);
+    if (rc) return rc;
+    ns->h_n_evals += (long long)ns->h_k_last *
+                     (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
+    return end_walk_launch(ns, st);
+}
+
+}  // namespace gl
+
+extern "C" {
+
+int64_t gl_ns_workspace_bytes(const gl_ns_config *cfg, int32_t d) {
+    if (gl::check_config(cfg, d)) return GL_EINVAL;
+    return (int64_t)gl::workspace_layout(*cfg, d).total;
+}
+
+int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
+                 const gl_ns_buffers *b, gl_ns **out) {
+    int rc = gl::check_config(cfg, d);
+    if (rc) return rc;
+    GL_REQUIRE(out != nullptr, "out is NULL");
+    GL_REQUIRE(priors_host != nullptr && model != nullptr && b != nullptr, "NULL argument");
+    GL_REQUIRE(model->dev.d == d, "model dimension %d != number of sampled parameters %d", model->dev.d, d);
+    GL_REQUIRE(b->live && b->logl && b->dead_x && b->dead_logl && b->dead_w && b->dead_idx && b->dead_step &&
+                   b->workspace,
+               "NULL device buffer");
+    for (int j = 0; j < d; ++j) {
+        GL_REQUIRE(priors_host[j].kind >= GL_PRIOR_UNIFORM && priors_host[j].kind <= GL_PRIOR_LOGUNIFORM,
+                   "prior %d: unknown kind %d", j, priors_host[j].kind);
+    }
+    int dev = 0;
+    GL_CUDA(cudaGetDevice(&dev));          // fail loudly when no device is usable
+    gl_ns *ns = new (std::nothrow) gl_ns();
+    if (!ns) return GL_ENOMEM;
+    ns->cfg = *cfg;
+    ns->d = d;
+    ns->model = model->dev;
+    ns->model_handle = model;
+    memcpy(ns->priors, priors_host, sizeof(gl_prior) * d);
+    ns->buf = *b;
+    const gl::WorkspaceLayout L = gl::workspace_layout(*cfg, d);
+    char *w = (char *)b->workspace;
+    ns->S = (gl::EngineState *)(w + L.off_state);
+    ns->sel = (gl::SelectState *)(w + L.off_sel);
+    ns->pt = (gl::PriorTable *)(w + L.off_pt);
+    ns->dead_list = (long long *)(w + L.off_list);
+    ns->is_dead = (unsigned char *)(w + L.off_isdead);
+    ns->scratch_x = (double *)(w + L.off_sx);
+    ns->scratch_l = (double *)(w + L.off_sl);
+    ns->tmp_k = (double *)(w + L.off_tmp);
+    ns->fin_partials = (double *)(w + L.off_fin);
+    ns->h_n_dead = ns->h_n_evals = 0;
+    ns->h_step = ns->h_k_last = 0;
+    ns->initialized = ns->pending_refill = ns->finalized = false;
+    *out = ns;
+    return GL_OK;
+}
+
+int gl_ns_destroy(gl_ns *ns) {
+    delete ns;
+    return GL_OK;
+}
+
+int gl_ns_init(gl_ns *ns, int32_t skip_population, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const gl::WorkspaceLayout L = gl::workspace_layout(ns->cfg, ns->d);
+    GL_CUDA(cudaMemsetAsync(ns->buf.workspace, 0, L.total, st));
+    gl::EngineState h;
+    memset(&h, 0, sizeof(h));
+    h.M = -INFINITY;
+    h.lstar = -INFINITY;
+    GL_CUDA(cudaMemcpyAsync(ns->S, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    gl::PriorTable pt;
+    memset(&pt, 0, sizeof(pt));
+    for (int j = 0; j < ns->d; ++j) {
+        pt.kind[j] = ns->priors[j].kind;
+        pt.p0[j] = ns->priors[j].p0;
+        pt.p1[j] = ns->priors[j].p1;
+    }
+    GL_CUDA(cudaMemcpyAsync(ns->pt, &pt, sizeof(pt), cudaMemcpyHostToDevice, st));
+    GL_CUDA(cudaStreamSynchronize(st));    // h / pt are stack objects
+    const long long N = ns->cfg.population_size;
+    if (!skip_population) {
+        int rc = gl::prior_draw_launch(ns->priors, ns->d, ns->cfg.seed, gl::GL_TAG_INIT, ns->cfg.row_offset, N,
+                                       ns->buf.live, st);
+        if (rc) return rc;
+        rc = gl::loglike_eval_launch(ns->model_handle, ns->buf.live, N, ns->buf.logl, st);
+        if (rc) return rc;
+        ns->h_n_evals = N;
+    } else {
+        ns->h_n_evals = 0;
+    }
+    gl::init_widths_kernel<<<ns->d, 128, 0, st>>>(ns->S, ns->pt, ns->d, ns->cfg.seed);
+    GL_CHECK_LAUNCH();
+    ns->h_n_dead = 0;
+    ns->h_step = ns->h_k_last = 0;
+    ns->initialized = true;
+    ns->pending_refill = ns->finalized = false;
+    return GL_OK;
+}
+
+int gl_ns_kill(gl_ns *ns, int32_t k, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (!ns->initialized || ns->finalized || ns->pending_refill) {
+        gl::set_error("gl_ns_kill: call gl_ns_init first / refill the previous batch / not after finalize");
+        return GL_ESTATE;
+    }
+    GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k, "k=%d outside [1, batch_k=%d]", k, ns->cfg.batch_k);
+    return gl::kill_launch(ns, k, INT64_MAX, (cudaStream_t)stream);
+}
+
+int gl_ns_refill(gl_ns *ns, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (!ns->pending_refill || ns->finalized) {
+        gl::set_error("gl_ns_refill: no batch is waiting for replacement");
+        return GL_ESTATE;
+    }
+    return gl::refill_launch(ns, (cudaStream_t)stream);
+}
+
+int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_dev, int32_t k, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (!ns->pending_refill || ns->finalized) {
+        gl::set_error("gl_ns_inject: no batch is waiting for replacement");
+        return GL_ESTATE;
+    }
+    GL_REQUIRE(k == ns->h_k_last, "k=%d but the waiting batch has %d slots", k, ns->h_k_last);
+    GL_REQUIRE(points_dev && logl_dev, "NULL device pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = gl::blocks_for(k, 256, 4);
+    gl::gather_logl_kernel<<<blocks, 256, 0, st>>>(ns->S, ns->dead_list, ns->buf.logl, ns->tmp_k);
+    gl::inject_kernel<<<blocks, 256, 0, st>>>(ns->S, ns->dead_list, ns->tmp_k, points_dev, logl_dev, ns->d,
+                                              ns->buf.live, ns->buf.logl);
+    GL_CHECK_LAUNCH();
+    return gl::end_walk_launch(ns, st);
+}
+
+int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (!ns->initialized || ns->finalized) {
+        gl::set_error("gl_ns_advance: engine not initialised or already finalized");
+        return GL_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ns->pending_refill && ns->h_n_dead < n_deaths_total) {
+        int rc = gl::refill_launch(ns, st);
+        if (rc) return rc;
+    }
+    while (ns->h_n_dead < n_deaths_total) {
+        int rc = gl::kill_launch(ns, ns->cfg.batch_k, n_deaths_total, st);
+        if (rc) return rc;
+        if (ns->h_k_last <= 0) break;
+        if (ns->h_n_dead < n_deaths_total) {
+            rc = gl::refill_launch(ns, st);
+            if (rc) return rc;
+        }
+    }
+    return GL_OK;
+}
+
+int gl_ns_finalize(gl_ns *ns, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (!ns->initialized || ns->finalized) {
+        gl::set_error("gl_ns_finalize: engine not initialised or already finalized");
+        return GL_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = ns->cfg.population_size;
+    long long blocks = (N + 4095) / 4096;
+    if (blocks > gl::FIN_MAX_BLOCKS) blocks = gl::FIN_MAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    long long chunk = (N + blocks - 1) / blocks;
+    blocks = (N + chunk - 1) / chunk;
+    gl::final_partial_kernel<<<(int)blocks, gl::FIN_THREADS, 0, st>>>(ns->buf.logl, ns->is_dead, N, chunk,
+                                                                      ns->fin_partials);
+    gl::final_combine_kernel<<<1, 1, 0, st>>>(ns->S, ns->fin_partials, (int)blocks);
+    gl::final_rows_kernel<<<gl::blocks_for(N, 256, 8), 256, 0, st>>>(
+        ns->S, ns->dead_list, ns->is_dead, ns->buf.live, ns->buf.logl, N, ns->d, ns->cfg.row_offset,
+        ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
+        ns->buf.dead_step);
+    gl::final_done_kernel<<<1, 1, 0, st>>>(ns->S, ns->cfg.dead_capacity);
+    GL_CHECK_LAUNCH();
+    ns->finalized = true;
+    return GL_OK;
+}
+
+int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
+    GL_REQUIRE(ns != nullptr && out != nullptr, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    gl::EngineState h;
+    GL_CUDA(cudaMemcpyAsync(&h, ns->S, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GL_CUDA(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    out->n_dead = h.n_dead;
+    out->n_rows = h.n_rows;
+    out->n_evals = ns->h_n_evals;
+    out->step = h.step;
+    out->finalized = h.finalized;
+    out->log_x = h.logX;
+    out->lstar = h.lstar;
+    out->z_linear = h.Z_lin;
+    out->h_linear = h.H_lin;
+    out->lse_m = h.M;
+    out->lse_z = h.Zs;
+    out->lse_h = h.Hs;
+    if (h.Zs > 0.0) {
+        out->log_z = h.M + log(h.Zs);
+        out->information = -out->log_z + h.Hs / h.Zs;
+    } else {
+        out->log_z = -INFINITY;
+        out->information = 0.0;
+    }
+    memcpy(out->widths, h.widths, sizeof(double) * GL_MAX_DIM);
+    return GL_OK;
+}
+
+}  // extern "C"

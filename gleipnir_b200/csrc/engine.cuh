@@ -1,0 +1,67 @@
+// Device-resident state of one Nested Sampling run (NestedSampling.run,
+// nested_sampling.py:83-213) and the launch interfaces between the engine's parts.
+#pragma once
+#include "common.cuh"
+#include "likelihoods.cuh"
+#include "priors.cuh"
+#include "select.cuh"
+
+namespace gl {
+
+struct EngineState {                 // one instance in device memory per engine
+    long long n_dead;                // `_n_iterations`: deaths recorded
+    long long n_rows;                // valid rows in the dead buffers
+    int step;                        // batches whose refill has completed (Philox counter word)
+    int k_cur;                       // size of the current batch (0 = nothing to do)
+    int do_walk;                     // current batch is to be refilled
+    int finalized;
+    double logX;                     // ln remaining prior mass
+    double lstar;                    // likelihood wall of the current batch
+    double Z_lin, H_lin;             // reference's linear-space accumulators
+    double M, Zs, Hs;                // scaled accumulators: Z = Zs*e^M, H = Hs*e^M
+    double widths[GL_MAX_DIM];       // persisted proposal widths (`_widths`)
+    unsigned int acc[GL_MAX_TUNING_CYCLES][GL_MAX_DIM];   // pooled acceptance counts of this step
+    // finalize scratch
+    double fin_m, fin_s, fin_lin;
+    long long fin_n;
+};
+
+struct WalkParams {                  // by-value kernel parameter
+    EngineState *S;
+    const long long *dead_list;      // [k_cur] local slots of the current batch, ascending
+    const unsigned char *is_dead;    // [N] 1 for slots in dead_list
+    double *live;                    // [N, d]
+    double *logl;                    // [N]
+    const PriorTable *priors;        // device
+    double *scratch_x;               // [k_max, d] walker positions between tuning cycles
+    double *scratch_l;               // [k_max]
+    long long N;                     // local population
+    long long row_offset;
+    uint64_t seed;
+    int d, iterations, burn_in, tuning_cycles, proposal, k_max;
+};
+
+// walker.cu
+int walk_launch(const WalkParams &P, const ModelDev &M, cudaStream_t st);
+int walker_smem_bytes(int d, int threads);
+
+// loglike.cu / priors.cu
+int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, double *logl_dev, cudaStream_t st);
+int prior_draw_launch(const gl_prior *priors, int d, uint64_t seed, uint32_t tag, long long first_row,
+                      long long n_rows, double *x_dev, cudaStream_t st);
+
+// Proposal widths entering phase `phase` of the current step: the persisted widths adapted by
+// the pooled acceptance of the tuning cycles already run (x0.66 below 0.2, x1.33 above 0.6;
+// docstring semantics of samplers.py:26-30).
+__device__ __forceinline__ double phase_width(const EngineState *S, int j, int phase, int n_walkers) {
+    double w = S->widths[j];
+    const double denom = 20.0 * (double)n_walkers;
+    for (int c = 0; c < phase; ++c) {
+        const double rate = (double)S->acc[c][j] / denom;
+        if (rate < 0.2) w = w * 0.66;
+        else if (rate > 0.6) w = w * 1.33;
+    }
+    return w;
+}
+
+}  // namespace gl

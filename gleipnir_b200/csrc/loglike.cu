@@ -1,0 +1,149 @@
+// Model handles + the batched log-likelihood evaluation kernel
+// (replaces the N scalar `loglikelihood(row)` calls of nested_sampling.py:108).
+#include "common.cuh"
+#include "likelihoods.cuh"
+
+namespace gl {
+
+// One thread per parameter vector; rows are read straight from global memory (for the
+// small-d analytic models a row is 16-40 B, the whole array streams through L1 once).
+template <class Like>
+__global__ void __launch_bounds__(256) loglike_rows_kernel(ModelDev M, const double *__restrict__ x, long long n,
+                                                           double *__restrict__ out) {
+    const Like like(M);
+    const int d = M.d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = like.eval(x + i * d, 1);
+}
+
+struct EvalLauncher {
+    const gl_model *m;
+    const double *x;
+    long long n;
+    double *out;
+    cudaStream_t st;
+    template <class Like>
+    int operator()() {
+        long long blocks = (n + 255) / 256;
+        long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        loglike_rows_kernel<Like><<<(int)blocks, 256, 0, st>>>(m->dev, x, n, out);
+        GL_CHECK_LAUNCH();
+        return GL_OK;
+    }
+};
+
+int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, double *logl_dev, cudaStream_t st) {
+    GL_REQUIRE(m != nullptr, "model is NULL");
+    if (n <= 0) return GL_OK;
+    GL_REQUIRE(x_dev != nullptr && logl_dev != nullptr, "NULL device pointer");
+    EvalLauncher L{m, x_dev, n, logl_dev, st};
+    return dispatch_model(m->dev.kind, L);
+}
+
+static int new_model(int kind, int d, gl_model **out) {
+    GL_REQUIRE(out != nullptr, "out is NULL");
+    GL_REQUIRE(d >= 1 && d <= GL_MAX_DIM, "d=%d outside [1, %d]", d, GL_MAX_DIM);
+    gl_model *m = new gl_model();
+    memset(m, 0, sizeof(*m));
+    m->dev.kind = kind;
+    m->dev.d = d;
+    *out = m;
+    return GL_OK;
+}
+
+}  // namespace gl
+
+extern "C" {
+
+int gl_model_create_iid_gaussian(int32_t d, double mu, double sigma, gl_model **out) {
+    GL_REQUIRE(sigma > 0.0, "sigma must be > 0");
+    int rc = gl::new_model(GL_MODEL_IID_GAUSSIAN, d, out);
+    if (rc) return rc;
+    (*out)->dev.s0 = mu;
+    (*out)->dev.s1 = sigma;
+    (*out)->dev.s2 = (double)d * (-GL_HALF_LOG_2PI - log(sigma));
+    return GL_OK;
+}
+
+int gl_model_create_eggcarton(int32_t d, gl_model **out) { return gl::new_model(GL_MODEL_EGGCARTON, d, out); }
+
+int gl_model_create_mixture1d(const double *positions_host, int32_t n_positions, double width, gl_model **out) {
+    GL_REQUIRE(positions_host != nullptr && n_positions >= 1, "need >= 1 position");
+    GL_REQUIRE(width > 0.0, "width must be > 0");
+    int rc = gl::new_model(GL_MODEL_MIXTURE1D, 1, out);
+    if (rc) return rc;
+    gl_model *m = *out;
+    cudaError_t e = cudaMalloc(&m->aux_alloc, sizeof(double) * n_positions);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(m->aux_alloc, positions_host, sizeof(double) * n_positions, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(m->aux_alloc);
+        delete m;
+        *out = nullptr;
+        return gl::cuda_fail(e, "mixture1d upload", __FILE__, __LINE__);
+    }
+    m->dev.s0 = width;
+    m->dev.s1 = 1.0 / sqrt(2.0 * M_PI * width * width);
+    m->dev.n_aux = n_positions;
+    m->dev.aux0 = m->aux_alloc;
+    return GL_OK;
+}
+
+int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const double *P_host, double log_norm,
+                                   gl_model **out) {
+    GL_REQUIRE(mu_host != nullptr && P_host != nullptr, "mu/P is NULL");
+    int rc = gl::new_model(GL_MODEL_DENSE_GAUSSIAN, d, out);
+    if (rc) return rc;
+    gl_model *m = *out;
+    const size_t nd = (size_t)d, bytes = sizeof(double) * (nd + nd * nd);
+    cudaError_t e = cudaMalloc(&m->aux_alloc, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(m->aux_alloc, mu_host, sizeof(double) * nd, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(m->aux_alloc + nd, P_host, sizeof(double) * nd * nd, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(m->aux_alloc);
+        delete m;
+        *out = nullptr;
+        return gl::cuda_fail(e, "dense gaussian upload", __FILE__, __LINE__);
+    }
+    m->dev.s0 = log_norm;
+    m->dev.aux0 = m->aux_alloc;
+    m->dev.aux1 = m->aux_alloc + nd;
+    return GL_OK;
+}
+
+int gl_model_dim(const gl_model *m) { return m ? m->dev.d : GL_EINVAL; }
+int gl_model_kind_of(const gl_model *m) { return m ? m->dev.kind : GL_EINVAL; }
+
+int gl_model_destroy(gl_model *m) {
+    if (!m) return GL_OK;
+    if (m->aux_alloc) cudaFree(m->aux_alloc);
+    delete m;
+    return GL_OK;
+}
+
+int gl_loglike_eval(const gl_model *m, const double *x_dev, int64_t n, double *logl_dev, void *stream) {
+    return gl::loglike_eval_launch(m, x_dev, n, logl_dev, (cudaStream_t)stream);
+}
+
+int gl_loglike_eval_host(const gl_model *m, const double *x_host, int64_t n, double *logl_host) {
+    GL_REQUIRE(m != nullptr, "model is NULL");
+    if (n <= 0) return GL_OK;
+    GL_REQUIRE(x_host != nullptr && logl_host != nullptr, "NULL host pointer");
+    const size_t d = (size_t)m->dev.d;
+    double *buf = nullptr;
+    GL_CUDA(cudaMalloc(&buf, sizeof(double) * (n * d + n)));
+    cudaError_t e = cudaMemcpy(buf, x_host, sizeof(double) * n * d, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? gl::loglike_eval_launch(m, buf, n, buf + n * d, 0)
+                              : gl::cuda_fail(e, "H2D", __FILE__, __LINE__);
+    if (rc == GL_OK) {
+        e = cudaMemcpy(logl_host, buf + n * d, sizeof(double) * n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = gl::cuda_fail(e, "D2H", __FILE__, __LINE__);
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Closed-form prior pdf / ppf for the three recognised scipy.stats families
+// (SampledParameter, gleipnir/sampled_parameter.py:40-80).  Arithmetic forms match
+// oracle/priors.py.
+#pragma once
+#include "common.cuh"
+
+namespace gl {
+
+struct PriorTable {   // device copy, SoA
+    int32_t kind[GL_MAX_DIM];
+    double p0[GL_MAX_DIM];
+    double p1[GL_MAX_DIM];
+};
+
+#define GL_LOG_SQRT_2PI 0.91893853320467274178
+
+__device__ __forceinline__ double prior_pdf(int kind, double p0, double p1, double x) {
+    if (kind == GL_PRIOR_UNIFORM) {
+        if (x != x) return x;
+        double y = (x - p0) / p1;
+        return (y >= 0.0 && y <= 1.0) ? 1.0 / p1 : 0.0;
+    } else if (kind == GL_PRIOR_NORM) {
+        double z = (x - p0) / p1;
+        return exp(-0.5 * z * z - GL_LOG_SQRT_2PI) / p1;
+    } else {
+        if (x != x) return x;
+        return (x >= p0 && x <= p1) ? 1.0 / (x * log(p1 / p0)) : 0.0;
+    }
+}
+
+__device__ __forceinline__ double prior_ppf(int kind, double p0, double p1, double u) {
+    if (kind == GL_PRIOR_UNIFORM) {
+        return u * p1 + p0;
+    } else if (kind == GL_PRIOR_NORM) {
+        return normcdfinv(u) * p1 + p0;
+    } else {
+        return p0 * exp(u * log(p1 / p0));
+    }
+}
+
+}  // namespace gl

@@ -1,0 +1,131 @@
+"""``DeviceEngine`` -- thin Python handle on the C-ABI Nested Sampling engine
+(``gl_ns_*`` in ``include/gleipnir_b200.h``).  torch provides device memory and the
+stream; every kernel is ours.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.GleipnirB200Error("no CUDA device is available and gleipnir_b200 has no CPU fallback")
+    return torch
+
+
+class DeviceEngine(object):
+    """One device-resident NS run: live set, dead-point log, accumulators, widths."""
+
+    def __init__(self, prior_table, model_handle, population_size, batch_k, n_deaths_capacity, iterations=100,
+                 burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.d = len(prior_table)
+        self.N = int(population_size)
+        self.device = torch.device("cuda" if device is None else device)
+        cap = int(n_deaths_capacity) + self.N
+        self.cfg = _lib.gl_ns_config(population_size=self.N, batch_k=int(batch_k), iterations=int(iterations),
+                                     burn_in=int(burn_in), tuning_cycles=int(tuning_cycles),
+                                     proposal=int(proposal), reserved=0, seed=int(seed) & (2 ** 64 - 1),
+                                     dead_capacity=cap, row_offset=0, global_population=self.N)
+        ws = self.lib.gl_ns_workspace_bytes(ctypes.byref(self.cfg), self.d)
+        if ws < 0:
+            _lib.check(int(ws))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.live = torch.empty((self.N, self.d), **f64)
+        self.logl = torch.empty(self.N, **f64)
+        self.dead_x = torch.empty((cap, self.d), **f64)
+        self.dead_logl = torch.empty(cap, **f64)
+        self.dead_w = torch.empty(cap, **f64)
+        self.dead_idx = torch.empty(cap, dtype=torch.int64, device=self.device)
+        self.dead_step = torch.empty(cap, dtype=torch.int32, device=self.device)
+        self.workspace = torch.empty(int(ws), dtype=torch.uint8, device=self.device)
+        self._bufs = _lib.gl_ns_buffers(self.live.data_ptr(), self.logl.data_ptr(), self.dead_x.data_ptr(),
+                                        self.dead_logl.data_ptr(), self.dead_w.data_ptr(),
+                                        self.dead_idx.data_ptr(), self.dead_step.data_ptr(),
+                                        self.workspace.data_ptr())
+        self._priors = _lib.prior_array(prior_table)
+        self._model = model_handle
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.gl_ns_create(ctypes.byref(self.cfg), self._priors, self.d, model_handle,
+                                         ctypes.byref(self._bufs), ctypes.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.gl_ns_destroy(h)
+            self._h = ctypes.c_void_p()
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def init(self, live=None, logl=None):
+        """Draw + evaluate the initial population (or adopt a caller-supplied one)."""
+        torch = _torch()
+        skip = 0
+        if live is not None:
+            self.live.copy_(torch.as_tensor(np.asarray(live, dtype=np.float64)).to(self.device))
+            self.logl.copy_(torch.as_tensor(np.asarray(logl, dtype=np.float64)).to(self.device))
+            skip = 1
+        _lib.check(self.lib.gl_ns_init(self._h, skip, self._stream()))
+
+    def advance(self, n_deaths_total):
+        _lib.check(self.lib.gl_ns_advance(self._h, int(n_deaths_total), self._stream()))
+
+    def kill(self, k):
+        _lib.check(self.lib.gl_ns_kill(self._h, int(k), self._stream()))
+
+    def refill(self):
+        _lib.check(self.lib.gl_ns_refill(self._h, self._stream()))
+
+    def inject(self, points, logls):
+        torch = _torch()
+        p = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64)).to(self.device)
+        l = torch.as_tensor(np.ascontiguousarray(logls, dtype=np.float64)).to(self.device)
+        _lib.check(self.lib.gl_ns_inject(self._h, p.data_ptr(), l.data_ptr(), int(l.numel()), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()     # p, l must outlive the kernels
+
+    def finalize(self):
+        _lib.check(self.lib.gl_ns_finalize(self._h, self._stream()))
+
+    def state(self):
+        st = _lib.gl_ns_state()
+        _lib.check(self.lib.gl_ns_read_state(self._h, ctypes.byref(st), self._stream()))
+        return st
+
+    def dead_table(self):
+        """Dead-point log as a host array [rows, d+2] (log_l, weight, x...) in death order,
+        plus the slot index and batch id of every row."""
+        torch = _torch()
+        st = self.state()
+        rows = int(st.n_rows)
+        logl = self.dead_logl[:rows].cpu().numpy()
+        w = self.dead_w[:rows].cpu().numpy()
+        x = self.dead_x[:rows].cpu().numpy()
+        idx = self.dead_idx[:rows].cpu().numpy()
+        step = self.dead_step[:rows].cpu().numpy()
+        order = death_order(logl, idx, step)
+        table = np.concatenate((logl[order, None], w[order, None], x[order]), axis=1)
+        return table, idx[order], step[order]
+
+
+def sort_key_host(logl):
+    """Host copy of the device ordering key (NaN first, -0.0 == +0.0)."""
+    x = np.asarray(logl, dtype=np.float64) + 0.0
+    b = x.view(np.uint64)
+    neg = (b >> np.uint64(63)).astype(bool)
+    k = np.where(neg, ~b, b | np.uint64(0x8000000000000000))
+    return np.where(np.isnan(x), np.uint64(0), k)
+
+
+def death_order(logl, idx, step):
+    """Permutation putting the device's dead rows (index order inside a batch) into death
+    order: batches in sequence, ascending (logL, slot) inside a batch, survivors (step -1)
+    last in slot order."""
+    step = np.asarray(step, dtype=np.int64)
+    batch = np.where(step < 0, np.iinfo(np.int64).max, step)
+    key = np.where(step < 0, np.uint64(0), sort_key_host(logl))
+    return np.lexsort((idx, key, batch))

@@ -1,0 +1,245 @@
+"""``NestedSampling`` -- drop-in for ``gleipnir.nestedsampling.NestedSampling``
+(``gleipnir/nestedsampling/nested_sampling.py:22-350``) whose ``run()`` executes on a B200.
+
+Same constructor, ``run(verbose=False) -> (log_evidence, log_evidence_error)``, read-only
+properties (``evidence``, ``evidence_error``, ``log_evidence``, ``log_evidence_error``,
+``information``, ``dead_points``), ``posteriors``, ``max_loglikelihood``, ``deviance_ic``,
+``best_fit_likelihood`` and the inherited ABC helpers.  Extra keyword arguments (all
+optional, defaults keep the reference call verbatim):
+
+    batch_k   deaths per device step.  1 reproduces upstream's one-death-per-iteration
+              sequencing exactly; the default ``None`` picks ``max(1, N // 10)``.
+    seed      Philox key.  Default: drawn from numpy's global RNG, so ``np.random.seed``
+              still makes a script reproducible.
+    device    torch device (default: current CUDA device).
+
+The whole run -- prior draws, log-likelihoods, k-worst selection, evidence / information
+accumulation, constrained Metropolis walkers, stop test -- is device resident (see
+``csrc/engine.cu``); the host only converts the stopping criterion into a death count and
+copies the dead-point log back at the end.
+"""
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from ..engine import DeviceEngine
+from ..likelihoods import require_device_loglikelihood
+from ..nsbase import NestedSamplingBase
+from ..sampled_parameter import prior_table
+from .samplers import MetropolisComponentWiseHardNSRejection
+from .stopping_criterion import NumberOfIterations
+
+
+def _default_sampler():
+    return MetropolisComponentWiseHardNSRejection(10, tuning_cycles=1)
+
+
+class NestedSampling(NestedSamplingBase):
+
+    def __init__(self, sampled_parameters, loglikelihood, population_size, sampler=None,
+                 stopping_criterion=None, batch_k=None, seed=None, device=None):
+        self.sampled_parameters = sampled_parameters
+        self._sampled_parameters_dict = {sp.name: sp for sp in sampled_parameters}
+        self.loglikelihood = loglikelihood
+        # upstream's defaults (nested_sampling.py:51-52), but a fresh object per instance
+        # instead of a shared mutable default argument
+        self.sampler = sampler if sampler is not None else _default_sampler()
+        self.population_size = population_size
+        self.stopping_criterion = stopping_criterion if stopping_criterion is not None else NumberOfIterations(1000)
+        self.batch_k = batch_k
+        self.seed = seed
+        self.device = device
+
+        self._alpha = population_size / (population_size + 1)
+        self._evidence = 0.0
+        self._evidence_error = 0.0
+        self._logZ_err = 0.0
+        self._log_evidence = 0.0
+        self._information = 0.0
+        self._H = 0.0
+        self._n_iterations = 0
+        self._n_evals = 0
+        self._dead_points = list()
+        self._live_points = None
+        self._post_eval = False
+        self._posteriors = None
+        self._engine = None
+        self._state = None
+
+    # ------------------------------------------------------------------------------------
+    def _resolve_batch_k(self):
+        n = int(self.population_size)
+        k = self.batch_k
+        if k is None:
+            k = max(1, n // 10)
+        k = int(k)
+        if not (1 <= k < n):
+            raise ValueError("batch_k must satisfy 1 <= batch_k < population_size")
+        return k
+
+    def _death_count(self):
+        crit = self.stopping_criterion
+        if hasattr(crit, "death_count"):
+            return int(crit.death_count(self))
+        return None
+
+    def run(self, verbose=False):
+        loglike = require_device_loglikelihood(self.loglikelihood)
+        if loglike.ndim != len(self.sampled_parameters):
+            raise ValueError("loglikelihood.ndim = %d but %d sampled parameters"
+                             % (loglike.ndim, len(self.sampled_parameters)))
+        table = prior_table(self.sampled_parameters)
+        n = int(self.population_size)
+        k = self._resolve_batch_k()
+        seed = self.seed
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+        scfg = self.sampler.device_config()
+        n_deaths = self._death_count()
+        chunked = n_deaths is None
+        if chunked:
+            # user-defined criterion: evaluated on the host between device batches
+            capacity = int(getattr(self.stopping_criterion, "max_iterations", 100 * n))
+        else:
+            capacity = n_deaths
+        if verbose:
+            print("Generating the initial set of live points with population size {}...".format(n))
+        eng = DeviceEngine(table, loglike.device_model(), n, k, capacity, seed=seed, device=self.device, **scfg)
+        self._engine = eng
+        if verbose:
+            print("Evaluating the loglikelihood function for each live point...")
+        eng.init()
+        if not chunked:
+            if verbose:
+                # progress printing needs host visibility: advance in slices of ~10 batches
+                done = 0
+                while done < n_deaths:
+                    done = min(n_deaths, done + 10 * k)
+                    eng.advance(done)
+                    st = eng.state()
+                    print("Iteration: {} Evidence estimate: {} Remaining prior mass: {}".format(
+                        st.n_dead, np.exp(st.log_z), np.exp(st.log_x)))
+            else:
+                eng.advance(n_deaths)
+        else:
+            done = 0
+            while done < capacity:
+                done = min(capacity, done + k)
+                eng.advance(done)
+                st = eng.state()
+                self._n_iterations = int(st.n_dead)
+                self._evidence = float(np.exp(st.log_z))
+                self._information = float(st.information)
+                if self._stopping_criterion():
+                    break
+        eng.finalize()
+        st = eng.state()
+        self._state = st
+        self._n_iterations = int(st.n_dead)
+        self._n_evals = int(st.n_evals)
+        self._log_evidence = float(st.log_z)
+        with np.errstate(over="ignore"):
+            self._evidence = float(np.exp(st.log_z))
+        self._information = float(st.information)
+        self._H = float(st.h_linear)
+        self._logZ_err = float(np.sqrt(max(self._information, 0.0) / n))
+        self._evidence_error = float(np.exp(self._logZ_err))
+        table_rows, _idx, _step = eng.dead_table()
+        names = [sp.name for sp in self.sampled_parameters]
+        self._dead_points = pd.DataFrame(table_rows, columns=['log_l', 'weight'] + names)
+        self._live_points = pd.DataFrame(eng.live.cpu().numpy(), columns=names)
+        return self._log_evidence, self._logZ_err
+
+    def _stopping_criterion(self):
+        return self.stopping_criterion(self)
+
+    # ---- read-only outputs (nested_sampling.py:219-264,338-344) ------------------------------
+    @property
+    def evidence(self):
+        return self._evidence
+
+    @evidence.setter
+    def evidence(self, value):
+        warnings.warn("evidence is not settable")
+
+    @property
+    def evidence_error(self):
+        return self._evidence_error
+
+    @evidence_error.setter
+    def evidence_error(self, value):
+        warnings.warn("evidence_error is not settable")
+
+    @property
+    def log_evidence(self):
+        return self._log_evidence
+
+    @log_evidence.setter
+    def log_evidence(self, value):
+        warnings.warn("log_evidence is not settable")
+
+    @property
+    def log_evidence_error(self):
+        return self._logZ_err
+
+    @log_evidence_error.setter
+    def log_evidence_error(self, value):
+        warnings.warn("log_evidence_error is not settable")
+
+    @property
+    def information(self):
+        return self._information
+
+    @information.setter
+    def information(self, value):
+        warnings.warn("information is not settable")
+
+    @property
+    def dead_points(self):
+        return self._dead_points
+
+    @dead_points.setter
+    def dead_points(self, value):
+        warnings.warn("dead_points is not settable")
+
+    # ---- post-processing (nested_sampling.py:266-336) ----------------------------------------
+    def _normalised_weights(self):
+        logl = self._dead_points['log_l'].to_numpy()
+        w = self._dead_points['weight'].to_numpy()
+        with np.errstate(all="ignore"):
+            nw = np.exp(np.log(w) + logl - self._log_evidence)     # = w*exp(logl)/Z without overflow
+        return logl, np.where(np.isnan(nw), 0.0, nw)
+
+    def posteriors(self, nbins=None):
+        """{name: (marginal, bin_edges, bin_centers)}: weighted histograms of the dead points
+        (Rice-rule bin count); cached after the first call, as upstream."""
+        if not self._post_eval:
+            _, nw = self._normalised_weights()
+            mask = nw > 0.0
+            if nbins is None:
+                nbins = 2 * int(np.cbrt(int(mask.sum())))
+            self._posteriors = dict()
+            for name in self._dead_points.columns[2:]:
+                marginal, edges = np.histogram(self._dead_points[name].to_numpy()[mask], weights=nw[mask],
+                                               density=True, bins=nbins)
+                self._posteriors[name] = (marginal, edges, (edges[:-1] + edges[1:]) / 2.0)
+            self._post_eval = True
+        return self._posteriors
+
+    def max_loglikelihood(self):
+        return self._dead_points['log_l'].max()
+
+    def deviance_ic(self):
+        """DIC = p_D + D_bar with D = -2 logL averaged over the posterior weights."""
+        logl, nw = self._normalised_weights()
+        mask = nw > 0.0
+        params = self._dead_points[self._dead_points.columns[2:]].to_numpy()
+        d_bar = np.average(-2.0 * logl[mask], weights=nw[mask])
+        theta_bar = np.average(params[mask], weights=nw[mask], axis=0)
+        p_d = d_bar - (-2.0 * self.loglikelihood(theta_bar))
+        return p_d + d_bar
+
+    def best_fit_likelihood(self):
+        vals = self._dead_points.to_numpy()
+        return vals[int(np.argmax(vals[:, 0]))][2:]

@@ -1,0 +1,214 @@
+/* gleipnir_b200 -- C ABI of the B200-native (sm_100a) Nested Sampling hot path.
+ *
+ * Drop-in boundary for the built-in classic Nested Sampling of LoLab-MSM/Gleipnir
+ * (reference: pure Python, no FFI of its own -- SURVEY 8b).  Every entry point
+ * names the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, `extern "C"`, pointers + sizes only; no torch / C++ types;
+ *   - `*_dev` pointers are CUDA device pointers owned by the caller (in the Python
+ *     host they are torch tensors); `*_host` are ordinary host pointers;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *     all device work is enqueued on it and NOT synchronised unless stated;
+ *   - every function returns GL_OK (0) or a negative GL_E* code; the message of the
+ *     last failure on the calling thread is returned by gl_last_error();
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with GL_ECUDA.
+ *   - all floating-point data is IEEE fp64; indices are int64 unless noted.
+ */
+#ifndef GLEIPNIR_B200_H
+#define GLEIPNIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GL_API __attribute__((visibility("default")))
+#else
+#define GL_API
+#endif
+
+#define GL_OK 0
+#define GL_EINVAL (-1)   /* bad argument */
+#define GL_ECUDA (-2)    /* CUDA runtime error / no device */
+#define GL_ESTATE (-3)   /* call out of order */
+#define GL_ENOMEM (-4)
+
+#define GL_MAX_DIM 128   /* sampled parameters per model */
+#define GL_MAX_TUNING_CYCLES 8
+
+/* ---- library ------------------------------------------------------------------ */
+GL_API int gl_abi_version(void);
+GL_API const char *gl_last_error(void);
+/* sm count / compute capability of the current device (GL_ECUDA when none). */
+GL_API int gl_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- priors: SampledParameter (gleipnir/sampled_parameter.py:21-80) ------------ */
+enum gl_prior_kind {
+    GL_PRIOR_UNIFORM = 0,    /* scipy.stats.uniform(loc=p0, scale=p1), closed support */
+    GL_PRIOR_NORM = 1,       /* scipy.stats.norm(loc=p0, scale=p1)                     */
+    GL_PRIOR_LOGUNIFORM = 2  /* scipy.stats.loguniform(a=p0, b=p1) (= reciprocal)      */
+};
+typedef struct gl_prior {
+    int32_t kind;
+    int32_t reserved;
+    double p0, p1;
+} gl_prior;
+
+/* SampledParameter.rvs (sampled_parameter.py:40-49) for a whole population:
+ * x[r, j] = ppf_j(u(seed, first_row + r, j)), row-major [n_rows, d]; Philox4x32-10,
+ * stream tag `tag` (GL_TAG_USER for user draws).  Replaces the N*d scalar rvs(1)
+ * calls of nested_sampling.py:93-101. */
+GL_API int gl_prior_draw(const gl_prior *priors_host, int32_t d, uint64_t seed, uint32_t tag,
+                  int64_t first_row, int64_t n_rows, double *x_dev, void *stream);
+/* SampledParameter.invcdf (sampled_parameter.py:72-80): out[i] = ppf(u[i]). */
+GL_API int gl_prior_ppf(const gl_prior *prior_host, const double *u_dev, double *out_dev, int64_t n, void *stream);
+/* SampledParameter.prior (sampled_parameter.py:62-70): out[i] = pdf(x[i]). */
+GL_API int gl_prior_pdf(const gl_prior *prior_host, const double *x_dev, double *out_dev, int64_t n, void *stream);
+/* SampledParameter.logprior (sampled_parameter.py:52-60): out[i] = log(pdf(x[i])). */
+GL_API int gl_prior_logpdf(const gl_prior *prior_host, const double *x_dev, double *out_dev, int64_t n, void *stream);
+/* Hypercube transform used by the third-party wrappers (multinest.py:131-132 etc.):
+ * x[r, j] = ppf_j(u[r, j]) for a whole [n, d] block. */
+GL_API int gl_prior_transform(const gl_prior *priors_host, int32_t d, const double *u_dev, double *x_dev, int64_t n_rows,
+                       void *stream);
+/* Host-buffer variants (copies inside; synchronous). */
+GL_API int gl_prior_ppf_host(const gl_prior *prior_host, const double *u_host, double *out_host, int64_t n);
+GL_API int gl_prior_pdf_host(const gl_prior *prior_host, const double *x_host, double *out_host, int64_t n);
+GL_API int gl_prior_logpdf_host(const gl_prior *prior_host, const double *x_host, double *out_host, int64_t n);
+
+/* ---- log-likelihood models: the batched device protocol ----------------------- */
+/* The reference's protocol is `loglikelihood(ndarray[d]) -> float`
+ * (nested_sampling.py:108, samplers.py:83,108,144).  A device model is an opaque
+ * handle; gl_loglike_eval is the batched form of that call. */
+typedef struct gl_model gl_model;
+
+enum gl_model_kind {
+    GL_MODEL_IID_GAUSSIAN = 0,  /* tests/test_nested_sampling.py:34-36                */
+    GL_MODEL_EGGCARTON = 1,     /* examples/eggcarton/NS_eggcarton.py:25-27          */
+    GL_MODEL_MIXTURE1D = 2,     /* examples/1d_multimodal/NS_1d_multimodal.py:20-32  */
+    GL_MODEL_DENSE_GAUSSIAN = 3 /* synthetic C3 (not in reference) */
+};
+
+/* -0.5*sum(((x-mu)/sigma)^2) - d*(0.5*log(2*pi) + log(sigma)) */
+GL_API int gl_model_create_iid_gaussian(int32_t d, double mu, double sigma, gl_model **out);
+/* (2 + prod_j cos(x_j))^5 */
+GL_API int gl_model_create_eggcarton(int32_t d, gl_model **out);
+/* log(mean_m N(x_0; positions[m], width)); NaN -> -inf.  d = 1. */
+GL_API int gl_model_create_mixture1d(const double *positions_host, int32_t n_positions, double width, gl_model **out);
+/* -0.5*(x-mu)^T P (x-mu) + log_norm; P row-major [d, d] symmetric. */
+GL_API int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const double *P_host, double log_norm,
+                                   gl_model **out);
+GL_API int gl_model_dim(const gl_model *m);
+GL_API int gl_model_kind_of(const gl_model *m);
+GL_API int gl_model_destroy(gl_model *m);
+
+/* logl[i] = loglikelihood(x[i, :]), x row-major [n, d]. */
+GL_API int gl_loglike_eval(const gl_model *m, const double *x_dev, int64_t n, double *logl_dev, void *stream);
+GL_API int gl_loglike_eval_host(const gl_model *m, const double *x_host, int64_t n, double *logl_host);
+
+/* ---- selection: np.argmin / k-worst (nested_sampling.py:115,156) -------------- */
+/* The k smallest of logl[0..n) under the order (value, index): NaN first (np.argmin
+ * semantics), -0.0 == +0.0, ties by lowest index.  Writes the k indices in ASCENDING
+ * INDEX order to idx_out_dev[0..k) and the largest selected value to *lstar_dev.
+ * `workspace_dev` must hold gl_select_workspace_bytes(n) bytes. */
+GL_API int64_t gl_select_workspace_bytes(int64_t n);
+GL_API int gl_select_kworst(const double *logl_dev, int64_t n, int32_t k, int64_t *idx_out_dev, double *lstar_dev,
+                     void *workspace_dev, void *stream);
+
+/* ---- the Nested Sampling engine: NestedSampling.run (nested_sampling.py:83-213) */
+enum gl_proposal_kind { GL_PROPOSAL_UNIFORM = 0, GL_PROPOSAL_NORMAL = 1 };
+
+typedef struct gl_ns_config {
+    int64_t population_size; /* N (nested_sampling.py:60)                                   */
+    int32_t batch_k;         /* deaths per step; 1 = the reference's sequencing              */
+    int32_t iterations;      /* samplers.py:41  MetropolisComponentWiseHardNSRejection attrs */
+    int32_t burn_in;         /* samplers.py:42                                               */
+    int32_t tuning_cycles;   /* samplers.py:43 (each cycle = 20 sweeps)                      */
+    int32_t proposal;        /* samplers.py:44  gl_proposal_kind                             */
+    int32_t reserved;
+    uint64_t seed;           /* Philox key                                                   */
+    int64_t dead_capacity;   /* rows the dead buffers can hold (>= n_deaths + N)             */
+    int64_t row_offset;      /* global index of local row 0 (multi-GPU shard), else 0        */
+    int64_t global_population; /* N summed over ranks (== population_size on one GPU)       */
+} gl_ns_config;
+
+/* Caller-owned device buffers (torch tensors in the Python host). */
+typedef struct gl_ns_buffers {
+    double *live;      /* [N, d]   row-major live points  (`_live_points`, nested_sampling.py:103) */
+    double *logl;      /* [N]      their log-likelihoods  (:108)                                   */
+    double *dead_x;    /* [dead_capacity, d]  dead-point parameter rows (:130-133,170-173)         */
+    double *dead_logl; /* [dead_capacity]     'log_l' column                                       */
+    double *dead_w;    /* [dead_capacity]     'weight' column                                      */
+    int64_t *dead_idx; /* [dead_capacity]     live slot each dead row came from                    */
+    int32_t *dead_step;/* [dead_capacity]     batch index of each dead row                         */
+    void *workspace;   /* gl_ns_workspace_bytes() bytes of scratch                                 */
+} gl_ns_buffers;
+
+/* Host-visible snapshot of the device-resident run state. */
+typedef struct gl_ns_state {
+    int64_t n_dead;       /* deaths recorded (`_n_iterations`)                          */
+    int64_t n_rows;       /* rows valid in the dead buffers (n_dead + survivors after finalize) */
+    int64_t n_evals;      /* log-likelihood evaluations performed on the device          */
+    int32_t step;         /* batches completed                                           */
+    int32_t finalized;
+    double log_x;         /* ln of remaining prior mass                                  */
+    double lstar;         /* current likelihood wall                                     */
+    double z_linear;      /* `_evidence` accumulated in linear space (nested_sampling.py:118-119) */
+    double h_linear;      /* `_H` in linear space (:121-123)                             */
+    double lse_m, lse_z, lse_h; /* scaled accumulators: Z = lse_z*exp(lse_m), H = lse_h*exp(lse_m) */
+    double log_z;         /* ln Z from the scaled accumulators                           */
+    double information;   /* -ln Z + H/Z (:125,167,194)                                  */
+    double widths[GL_MAX_DIM]; /* current proposal widths (`_widths`, samplers.py:50,124) */
+} gl_ns_state;
+
+typedef struct gl_ns gl_ns;
+
+GL_API int64_t gl_ns_workspace_bytes(const gl_ns_config *cfg, int32_t d);
+GL_API int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
+                 const gl_ns_buffers *buffers, gl_ns **out);
+GL_API int gl_ns_destroy(gl_ns *ns);
+
+/* nested_sampling.py:93-108 + samplers.py:70-81: draw the initial population with
+ * Philox, evaluate its log-likelihoods, initialise the proposal widths.  With
+ * `skip_population` != 0 the caller has already filled buffers.live / buffers.logl
+ * (replay tests) and only the widths/state are initialised. */
+GL_API int gl_ns_init(gl_ns *ns, int32_t skip_population, void *stream);
+
+/* Enqueue batches (select k worst -> record -> accumulate -> refill by walkers) until
+ * exactly `n_deaths_total` deaths have been recorded; the last batch is shortened as
+ * needed and is not refilled.  nested_sampling.py:111-181. */
+GL_API int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream);
+
+/* Decomposed step, for replay tests and the multi-GPU host loop:
+ *   gl_ns_kill   select + record + accumulate one batch of (at most) k deaths
+ *   gl_ns_refill run the walkers for the last batch (nested_sampling.py:145-154)
+ *   gl_ns_inject stand-in for the sampler: write caller-supplied replacement rows
+ *                (death order = ascending (logL, index)) into the last batch's slots */
+GL_API int gl_ns_kill(gl_ns *ns, int32_t k, void *stream);
+GL_API int gl_ns_refill(gl_ns *ns, void *stream);
+GL_API int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_dev, int32_t k, void *stream);
+
+/* nested_sampling.py:183-203: final live-point term; appends the survivors to the
+ * dead buffers in index order with weight X/(#survivors). */
+GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
+
+/* Copy the device state to the host (synchronises `stream`). */
+GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
+
+/* ---- whole run with HOST buffers (the end-to-end entry point) ------------------ */
+/* NestedSampling(...).run() through host memory: allocates device buffers, uploads
+ * the prior table, runs init/advance/finalize, downloads the dead table
+ * [n_rows, d+2] (columns log_l, weight, x_0..x_{d-1}, rows in death order) and the
+ * state.  `dead_host` must hold (n_deaths_total + N) * (d + 2) doubles. */
+GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
+                   int64_t n_deaths_total, double *dead_host, gl_ns_state *state_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLEIPNIR_B200_H */
