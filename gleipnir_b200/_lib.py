@@ -42,7 +42,8 @@ class gl_ns_buffers(Structure):
 
 
 class gl_ns_state(Structure):
-    _fields_ = [("n_dead", c_int64), ("n_rows", c_int64), ("n_evals", c_int64), ("step", c_int32),
+    _fields_ = [("n_dead", c_int64), ("n_rows", c_int64), ("n_evals", c_int64), ("n_launches", c_int64),
+                ("step", c_int32),
                 ("finalized", c_int32), ("log_x", c_double), ("lstar", c_double), ("z_linear", c_double),
                 ("h_linear", c_double), ("lse_m", c_double), ("lse_z", c_double), ("lse_h", c_double),
                 ("log_z", c_double), ("information", c_double), ("widths", c_double * GL_MAX_DIM)]
@@ -83,6 +84,9 @@ _SIGNATURES = {
     "gl_ns_inject": (c_int, [_P, _P, _P, c_int32, _P]),
     "gl_ns_finalize": (c_int, [_P, _P]),
     "gl_ns_read_state": (c_int, [_P, POINTER(gl_ns_state), _P]),
+    "gl_ns_profile_enable": (c_int, [_P, c_int32]),
+    "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
+    "gl_microbench_dfma": (c_int, [c_int32, c_int32, _P, POINTER(c_int64), _P]),
     "gl_ns_run_host": (c_int, [POINTER(gl_ns_config), POINTER(gl_prior), c_int32, _P, c_int64, POINTER(c_double),
                                POINTER(gl_ns_state)]),
 }

@@ -6,6 +6,7 @@
 // Per step:  begin -> select (8 launches, select.cu) -> record -> accumulate
 //            -> walkers (tuning_cycles + 1 launches, walker.cu) -> end_walk
 #include <new>
+#include <vector>
 #include "engine.cuh"
 #include "philox.cuh"
 
@@ -329,9 +330,13 @@ struct gl_ns {
     unsigned char *is_dead;
     double *scratch_x, *scratch_l, *tmp_k, *fin_partials;
     // host mirrors (deterministic arithmetic; no device reads needed to drive the loop)
-    long long h_n_dead, h_n_evals;
+    long long h_n_dead, h_n_evals, h_launches;
     int h_step, h_k_last;
     bool initialized, pending_refill, finalized;
+    // optional CUDA-event timing of the walker / select launches (bench roofline)
+    bool prof;
+    std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
+    long long prof_walk_launches, prof_sel_launches;
 };
 
 namespace gl {
@@ -404,11 +409,23 @@ static int blocks_for(long long items, int threads, int cap_per_sm) {
     return (int)b;
 }
 
+static void prof_mark(gl_ns *ns, std::vector<cudaEvent_t> &v, cudaStream_t st) {
+    if (!ns->prof || v.size() >= 16384) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    v.push_back(e);
+}
+
 static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
     const long long N = ns->cfg.population_size;
     begin_kernel<<<1, 1, 0, st>>>(ns->S, k_req, n_target, N);
+    prof_mark(ns, ns->ev_sel, st);
     int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
     if (rc) return rc;
+    prof_mark(ns, ns->ev_sel, st);
+    ns->prof_sel_launches += SEL_PASSES + 2;
+    ns->h_launches += 1 + SEL_PASSES + 2 + 2;     // begin + select + record + accumulate
     const double n_global = (double)ns->cfg.global_population;
     record_kernel<<<blocks_for((long long)k_req * ns->d, 256, 8), 256, 0, st>>>(
         ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
@@ -431,14 +448,19 @@ static int end_walk_launch(gl_ns *ns, cudaStream_t st) {
     end_walk_kernel<<<blocks_for(ns->cfg.batch_k, 256, 4), 256, 0, st>>>(ns->S, ns->dead_list, ns->is_dead, ns->d,
                                                                           ns->cfg.tuning_cycles);
     GL_CHECK_LAUNCH();
+    ns->h_launches += 1;
     ns->h_step += 1;
     ns->pending_refill = false;
     return GL_OK;
 }
 
 static int refill_launch(gl_ns *ns, cudaStream_t st) {
+    prof_mark(ns, ns->ev_walk, st);
     int rc = walk_launch(walk_params(ns), ns->model, st);
     if (rc) return rc;
+    prof_mark(ns, ns->ev_walk, st);
+    ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
+    ns->h_launches += ns->cfg.tuning_cycles + 1;
     ns->h_n_evals += (long long)ns->h_k_last *
                      (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
     return end_walk_launch(ns, st);
@@ -488,14 +510,20 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->scratch_l = (double *)(w + L.off_sl);
     ns->tmp_k = (double *)(w + L.off_tmp);
     ns->fin_partials = (double *)(w + L.off_fin);
-    ns->h_n_dead = ns->h_n_evals = 0;
+    ns->h_n_dead = ns->h_n_evals = ns->h_launches = 0;
     ns->h_step = ns->h_k_last = 0;
     ns->initialized = ns->pending_refill = ns->finalized = false;
+    ns->prof = false;
+    ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
 }
 
 int gl_ns_destroy(gl_ns *ns) {
+    if (ns) {
+        for (cudaEvent_t e : ns->ev_walk) cudaEventDestroy(e);
+        for (cudaEvent_t e : ns->ev_sel) cudaEventDestroy(e);
+    }
     delete ns;
     return GL_OK;
 }
@@ -527,9 +555,11 @@ int gl_ns_init(gl_ns *ns, int32_t skip_population, void *stream) {
         rc = gl::loglike_eval_launch(ns->model_handle, ns->buf.live, N, ns->buf.logl, st);
         if (rc) return rc;
         ns->h_n_evals = N;
+        ns->h_launches += 2;
     } else {
         ns->h_n_evals = 0;
     }
+    ns->h_launches += 1;
     gl::init_widths_kernel<<<ns->d, 128, 0, st>>>(ns->S, ns->pt, ns->d, ns->cfg.seed);
     GL_CHECK_LAUNCH();
     ns->h_n_dead = 0;
@@ -572,6 +602,7 @@ int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_dev, in
     gl::inject_kernel<<<blocks, 256, 0, st>>>(ns->S, ns->dead_list, ns->tmp_k, points_dev, logl_dev, ns->d,
                                               ns->buf.live, ns->buf.logl);
     GL_CHECK_LAUNCH();
+    ns->h_launches += 2;
     return gl::end_walk_launch(ns, st);
 }
 
@@ -620,6 +651,7 @@ int gl_ns_finalize(gl_ns *ns, void *stream) {
         ns->buf.dead_step);
     gl::final_done_kernel<<<1, 1, 0, st>>>(ns->S, ns->cfg.dead_capacity);
     GL_CHECK_LAUNCH();
+    ns->h_launches += 4;
     ns->finalized = true;
     return GL_OK;
 }
@@ -634,6 +666,7 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
     out->n_dead = h.n_dead;
     out->n_rows = h.n_rows;
     out->n_evals = ns->h_n_evals;
+    out->n_launches = ns->h_launches;
     out->step = h.step;
     out->finalized = h.finalized;
     out->log_x = h.logX;
@@ -651,6 +684,39 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
         out->information = 0.0;
     }
     memcpy(out->widths, h.widths, sizeof(double) * GL_MAX_DIM);
+    return GL_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gl_ns_profile_enable(gl_ns *ns, int32_t enable) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    ns->prof = enable != 0;
+    return GL_OK;
+}
+
+int gl_ns_profile_read(gl_ns *ns, double *walk_ms, int64_t *walk_launches, double *select_ms,
+                       int64_t *select_launches) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    auto total = [](std::vector<cudaEvent_t> &v, double *out) -> int {
+        double acc = 0.0;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float ms = 0.f;
+            GL_CUDA(cudaEventSynchronize(v[i + 1]));
+            GL_CUDA(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+            acc += ms;
+        }
+        if (out) *out = acc;
+        return GL_OK;
+    };
+    int rc = total(ns->ev_walk, walk_ms);
+    if (rc) return rc;
+    rc = total(ns->ev_sel, select_ms);
+    if (rc) return rc;
+    if (walk_launches) *walk_launches = ns->prof_walk_launches;
+    if (select_launches) *select_launches = ns->prof_sel_launches;
     return GL_OK;
 }
 

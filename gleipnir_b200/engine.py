@@ -91,6 +91,18 @@ class DeviceEngine(object):
     def finalize(self):
         _lib.check(self.lib.gl_ns_finalize(self._h, self._stream()))
 
+    def profile_enable(self, enable=True):
+        _lib.check(self.lib.gl_ns_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(walk_ms, walk_launches, select_ms, select_launches) from CUDA events recorded on the
+        launching stream around the walker / selection kernels."""
+        wm, sm_ = ctypes.c_double(0), ctypes.c_double(0)
+        wl, sl = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib.gl_ns_profile_read(self._h, ctypes.byref(wm), ctypes.byref(wl), ctypes.byref(sm_),
+                                               ctypes.byref(sl)))
+        return wm.value, wl.value, sm_.value, sl.value
+
     def state(self):
         st = _lib.gl_ns_state()
         _lib.check(self.lib.gl_ns_read_state(self._h, ctypes.byref(st), self._stream()))

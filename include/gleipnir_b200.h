@@ -154,6 +154,7 @@ typedef struct gl_ns_state {
     int64_t n_dead;       /* deaths recorded (`_n_iterations`)                          */
     int64_t n_rows;       /* rows valid in the dead buffers (n_dead + survivors after finalize) */
     int64_t n_evals;      /* log-likelihood evaluations performed on the device          */
+    int64_t n_launches;   /* kernels of this library launched for the run so far        */
     int32_t step;         /* batches completed                                           */
     int32_t finalized;
     double log_x;         /* ln of remaining prior mass                                  */
@@ -200,6 +201,14 @@ GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 /* Copy the device state to the host (synchronises `stream`). */
 GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
 
+/* Optional CUDA-event timing of the two kernel groups that dominate a step, recorded on the
+ * launching stream: walker launches (tuning_cycles+1 per step) and selection launches (8 per
+ * step).  gl_ns_profile_read synchronises on the recorded events and returns the summed
+ * device time (ms) and the number of launches covered. */
+GL_API int gl_ns_profile_enable(gl_ns *ns, int32_t enable);
+GL_API int gl_ns_profile_read(gl_ns *ns, double *walk_ms, int64_t *walk_launches, double *select_ms,
+                              int64_t *select_launches);
+
 /* ---- whole run with HOST buffers (the end-to-end entry point) ------------------ */
 /* NestedSampling(...).run() through host memory: allocates device buffers, uploads
  * the prior table, runs init/advance/finalize, downloads the dead table
@@ -207,6 +216,13 @@ GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
  * state.  `dead_host` must hold (n_deaths_total + N) * (d + 2) doubles. */
 GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
                    int64_t n_deaths_total, double *dead_host, gl_ns_state *state_out);
+
+/* ---- measurement helpers ------------------------------------------------------ */
+/* FP64 DFMA-pipe peak microbenchmark (roofline denominator for the walker / ODE kernels;
+ * MEASURED_PEAKS.json has no FP64 entry).  Enqueues `blocks` CTAs of 256 threads running
+ * `iters` x 8 independent DFMAs each; *flops_out = floating-point operations enqueued.
+ * `scratch_dev` must hold blocks*256 doubles.  Time it with CUDA events on `stream`. */
+GL_API int gl_microbench_dfma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream);
 
 #ifdef __cplusplus
 }

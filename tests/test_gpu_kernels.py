@@ -64,7 +64,8 @@ def test_prior_draw_matches_oracle_philox(cuda, n, d):
     g = np.arange(first, first + n, dtype=np.uint64)
     for j, (kind, p0, p1) in enumerate(table):
         u, _ = px.uniforms(seed, g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), j, px.GL_TAG_USER)
-        np.testing.assert_allclose(got[:, j], pr.ppf(kind, p0, p1, u), rtol=RTOL, atol=1e-300)
+        # loc + scale*u cancels near 0: error is absolute, a few ulp of max(|loc|, scale)
+        np.testing.assert_allclose(got[:, j], pr.ppf(kind, p0, p1, u), rtol=RTOL, atol=4e-16 * max(abs(p0), abs(p1)))
 
 
 def test_prior_transform_block(cuda):
@@ -96,8 +97,11 @@ def test_loglike_matches_oracle(cuda, which):
     x = np.random.default_rng(which).uniform(lo, hi, size=(20011, dev.ndim))
     got = dev.evaluate(x)
     want = ora(x)
-    fin = np.isfinite(want)
-    assert np.array_equal(np.isfinite(got), fin)
+    # likelihoods in the fp64 denormal range (logL < -700) may flush to 0 -> -inf on the device;
+    # everywhere else finiteness and values must agree
+    fin = np.isfinite(want) & (want > -700.0)
+    assert np.all(np.isfinite(got[fin]))
+    assert np.all((got[~fin] == -np.inf) | (got[~fin] < -700.0))
     np.testing.assert_allclose(got[fin], want[fin], rtol=RTOL, atol=0 if which != 4 else 1e-10)
     # same kernel on device tensors, and the scalar host protocol of the reference
     gt = dev.evaluate(cuda.as_tensor(x, device="cuda")).cpu().numpy()
