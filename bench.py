@@ -216,7 +216,8 @@ def run_b200_arm(args):
 
     def one_run(seed, profile=False):
         eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, iterations=w["iterations"],
-                           burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=seed)
+                           burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=seed,
+                           walker_lanes=args.walker_lanes)
         if profile:
             eng.profile_enable(True)
         flush.zero_()                      # evict L2 between timed iterations
@@ -324,6 +325,7 @@ def run_b200_arm(args):
                 warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=w["name"], population_per_gpu=N, batch_k=k, n_deaths=n_deaths,
+                            walker_lanes=args.walker_lanes or "auto",
                             sampler="MetropolisComponentWiseHardNSRejection(iterations=50, tuning_cycles=2)",
                             l2="flushed between timed runs (256 MB memset)",
                             parallelism="replicas" if world > 1 else "single"),
@@ -359,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-k", type=int, default=0)
+    ap.add_argument("--walker-lanes", type=int, default=0, help="lanes per walker (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -31,7 +31,7 @@ class gl_prior(Structure):
 
 class gl_ns_config(Structure):
     _fields_ = [("population_size", c_int64), ("batch_k", c_int32), ("iterations", c_int32),
-                ("burn_in", c_int32), ("tuning_cycles", c_int32), ("proposal", c_int32), ("reserved", c_int32),
+                ("burn_in", c_int32), ("tuning_cycles", c_int32), ("proposal", c_int32), ("walker_lanes", c_int32),
                 ("seed", c_uint64), ("dead_capacity", c_int64), ("row_offset", c_int64),
                 ("global_population", c_int64)]
 
@@ -84,6 +84,7 @@ _SIGNATURES = {
     "gl_ns_inject": (c_int, [_P, _P, _P, c_int32, _P]),
     "gl_ns_finalize": (c_int, [_P, _P]),
     "gl_ns_read_state": (c_int, [_P, POINTER(gl_ns_state), _P]),
+    "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
     "gl_microbench_dfma": (c_int, [c_int32, c_int32, _P, POINTER(c_int64), _P]),

@@ -121,6 +121,237 @@ __global__ void __launch_bounds__(1024) accumulate_kernel(EngineState *S, const 
     }
 }
 
+// ---- fused kill for small populations ---------------------------------------------------
+// begin + select + record + accumulate in ONE single-CTA launch when the N ordering keys fit
+// in shared memory (N <= KILL_SMALL_MAX_N): the keys are loaded once, the six radix-select
+// passes (4-bit digits counted in registers and reduced with warp REDUX -- shared-memory atomics
+// cost ~2 cycles per lane on this part and made an 11-bit histogram version 4x slower), the
+// ballot-based index-ordered compaction, the dead-row copy and the evidence update all run out
+// of shared memory.  Same arithmetic and same (value, index) order as the multi-launch path
+// (select.cu + record_kernel + accumulate_kernel); replaces 11 launches (~90 us per step at
+// N = 10^4, r01 baseline launch list) by one.
+constexpr int KILL_SMALL_THREADS = 1024;
+constexpr int KILL_SMALL_MAX_N = 24 * 1024;      // 192 KB of keys + 8 KB histogram + scratch
+
+__global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
+    EngineState *S, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
+    long long capacity, const double *__restrict__ live, const double *__restrict__ logl,
+    long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, double *__restrict__ dead_x,
+    double *__restrict__ dead_logl, double *__restrict__ dead_w, long long *__restrict__ dead_idx,
+    int *__restrict__ dead_step) {
+    extern __shared__ unsigned long long keys[];                 // [N]
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ double scratch[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = KILL_SMALL_THREADS / 32;
+
+    // ---- begin: batch size -------------------------------------------------------------------
+    long long kk = n_target - S->n_dead;
+    if (kk > k_req) kk = k_req;
+    if (kk > N - 1) kk = N - 1;
+    if (kk < 0) kk = 0;
+    const int k = (int)kk;
+    if (tid == 0) { S->k_cur = k; S->do_walk = 0; }
+    if (k <= 0) return;
+
+    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
+    __syncthreads();
+
+    // ---- radix select on 4-bit digits, NO atomics ------------------------------------------------
+    // (1) min/max key -> the leading nibbles they share are skipped; (2) per pass each thread counts
+    // its candidates' digits in two 64-bit words of 8-bit counters (<= 24 keys per thread), widened
+    // to 16-bit lanes and summed with warp REDUX, one thread per digit sums the 32 warps, and every
+    // thread scans the 16 totals redundantly (prefix / k_rem stay in registers: two barriers per
+    // pass); (3) the loop stops as soon as the boundary bucket is needed in full (always true once
+    // it holds one key), so a typical live set needs 3-5 passes, not 16.
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int i = tid; i < N; i += KILL_SMALL_THREADS) {
+        const unsigned long long key = keys[i];
+        kmin = key < kmin ? key : kmin;
+        kmax = key > kmax ? key : kmax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b2 = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b2 > kmax ? b2 : kmax;
+    }
+    unsigned long long *mm = reinterpret_cast<unsigned long long *>(hist);      // [2*NW] scratch
+    if (lane == 0) { mm[wid] = kmin; mm[NW + wid] = kmax; }
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+        const unsigned long long a = mm[w], b2 = mm[NW + w];
+        kmin = a < kmin ? a : kmin;
+        kmax = b2 > kmax ? b2 : kmax;
+    }
+    __syncthreads();
+    const unsigned long long diff = kmin ^ kmax;
+    const int first_pass = diff ? __clzll((long long)diff) >> 2 : 16;            // nibbles shared by all keys
+    unsigned long long prefix = first_pass ? kmin >> (64 - 4 * first_pass) : 0ull;
+    int k_rem = k;
+    int sel_shift = diff ? 0 : 0;              // granularity of the final comparison (bits dropped)
+    if (!diff) prefix = kmin;                  // every key equal: lowest indices die
+    for (int pass = first_pass; pass < 16; ++pass) {
+        const int shift = 60 - 4 * pass;
+        unsigned long long lo8 = 0ull, hi8 = 0ull;     // 8-bit counters: digits 0-7, 8-15
+        for (int i = tid; i < N; i += KILL_SMALL_THREADS) {
+            const unsigned long long key = keys[i];
+            if (pass == 0 || (key >> (shift + 4)) == prefix) {
+                const unsigned int dg = (unsigned int)(key >> shift) & 15u;
+                const unsigned long long inc = 1ull << ((dg & 7u) << 3);
+                if (dg < 8u) lo8 += inc; else hi8 += inc;
+            }
+        }
+        // widen to 16-bit lanes: pk[q] = (count of digit 2q) | (count of digit 2q+1) << 16
+        unsigned int pk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pk[q] = (unsigned int)((lo8 >> (16 * q)) & 0xffull) | ((unsigned int)((lo8 >> (16 * q + 8)) & 0xffull) << 16);
+            pk[4 + q] = (unsigned int)((hi8 >> (16 * q)) & 0xffull) | ((unsigned int)((hi8 >> (16 * q + 8)) & 0xffull) << 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pk[q] = __reduce_add_sync(0xffffffffu, pk[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hist[wid * 8 + q] = pk[q];
+        }
+        __syncthreads();
+        if (tid < 16) {
+            unsigned int tot = 0u;
+            for (int w = 0; w < NW; ++w) tot += (hist[w * 8 + (tid >> 1)] >> ((tid & 1) << 4)) & 0xffffu;
+            hist[NW * 8 + tid] = tot;
+        }
+        __syncthreads();
+        int run = 0, digit = 15, run_at = 0, c_at = 0;
+        bool found = false;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int cq = (int)hist[NW * 8 + q];
+            if (!found && run + cq >= k_rem) { found = true; digit = q; run_at = run; c_at = cq; }
+            run += cq;
+        }
+        prefix = (prefix << 4) | (unsigned long long)digit;
+        k_rem -= run_at;
+        sel_shift = shift;
+        __syncthreads();                           // hist is rewritten by the next pass
+        if (c_at == k_rem) break;                  // the whole boundary bucket dies: no finer digits needed
+    }
+    // selection: (key >> sel_shift) < prefix, plus the first r (by slot) of those == prefix
+    const unsigned long long T = prefix;
+    const int r = k_rem;
+
+    // ---- index-ordered compaction -> dead_list (ascending slot), is_dead flags -----------------
+    // warp w owns the contiguous slots [w*C, (w+1)*C): count, exchange totals, then place with
+    // ballot prefixes -- one barrier, no atomics.  Also finds L* = largest selected key.
+    const int C = (N + NW - 1) / NW;
+    const int lo = wid * C, hi = lo + C < N ? lo + C : N;
+    int my_lt = 0, my_eq = 0;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        const unsigned long long kh = i < hi ? keys[i] >> sel_shift : ~0ull;
+        my_lt += __popc(__ballot_sync(0xffffffffu, i < hi && kh < T));
+        my_eq += __popc(__ballot_sync(0xffffffffu, i < hi && kh == T));
+    }
+    if (lane == 0) { hist[wid] = (unsigned)my_lt; hist[NW + wid] = (unsigned)my_eq; }
+    __syncthreads();
+    int run_lt = 0, run_eq = 0;
+    for (int w = 0; w < wid; ++w) { run_lt += (int)hist[w]; run_eq += (int)hist[NW + w]; }
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    unsigned long long kstar = 0ull;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        const unsigned long long key = i < hi ? keys[i] : ~0ull;
+        const unsigned long long kh = i < hi ? key >> sel_shift : ~0ull;
+        const bool is_lt = i < hi && kh < T, is_eq = i < hi && kh == T;
+        const unsigned b_lt = __ballot_sync(0xffffffffu, is_lt), b_eq = __ballot_sync(0xffffffffu, is_eq);
+        const int lt_before = run_lt + __popc(b_lt & lanemask_lt);
+        const int eq_before = run_eq + __popc(b_eq & lanemask_lt);
+        if (is_lt || (is_eq && eq_before < r)) {
+            const int pos = lt_before + (eq_before < r ? eq_before : r);
+            dead_list[pos] = i;
+            is_dead[i] = 1;
+            kstar = key > kstar ? key : kstar;
+        }
+        run_lt += __popc(b_lt);
+        run_eq += __popc(b_eq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kstar, o);
+        kstar = a > kstar ? a : kstar;
+    }
+    __syncthreads();                               // hist (totals) fully consumed
+    if (lane == 0) mm[wid] = kstar;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+        const unsigned long long a = mm[w];
+        kstar = a > kstar ? a : kstar;
+    }
+
+    // ---- record (nested_sampling.py:130-133,170-173) --------------------------------------------
+    const long long base_row = S->n_rows;
+    const double logw = S->logX - log(n_global + 1.0);
+    const double w = exp(logw);
+    const bool room = base_row + k <= capacity;
+    if (room) {
+        const int step = S->step;
+        for (int e = tid; e < k * d; e += KILL_SMALL_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const long long slot = dead_list[q];
+            dead_x[(base_row + q) * d + j] = live[slot * d + j];
+            if (j == 0) {
+                dead_logl[base_row + q] = logl[slot];
+                dead_w[base_row + q] = w;
+                dead_idx[base_row + q] = slot + row_offset;
+                dead_step[base_row + q] = step;
+            }
+        }
+    }
+
+    // ---- accumulate (nested_sampling.py:118-125,160-167); same forms as accumulate_kernel -------
+    double mx = -INFINITY;
+    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
+        const double lw = logw + logl[dead_list[i]];
+        if (isfinite(lw)) mx = fmax(mx, lw);
+    }
+    mx = block_max(mx, scratch);
+    const double m_old = S->M;
+    const double m_new = fmax(m_old, mx);
+    double sz = 0.0, sh = 0.0, zl = 0.0, hl = 0.0;
+    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
+        const double L = logl[dead_list[i]];
+        const double lw = logw + L;
+        if (isfinite(lw)) {
+            const double t = exp(lw - m_new);
+            sz += t;
+            sh += t * L;
+        }
+        const double dZ = w * exp(L);
+        zl += dZ;
+        const double dH = dZ * L;
+        if (dH == dH) hl += dH;
+    }
+    sz = block_sum(sz, scratch);
+    sh = block_sum(sh, scratch);
+    zl = block_sum(zl, scratch);
+    hl = block_sum(hl, scratch);
+    if (tid == 0) {
+        if (mx > -INFINITY) {
+            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+            S->Zs = S->Zs * scale + sz;
+            S->Hs = S->Hs * scale + sh;
+            S->M = m_new;
+        }
+        S->Z_lin += zl;
+        S->H_lin += hl;
+        S->logX += log((n_global - (double)k + 1.0) / (n_global + 1.0));
+        S->n_dead += k;
+        if (room) S->n_rows += k;
+        S->lstar = key_to_double(kstar);
+        S->do_walk = S->n_dead < n_target;
+    }
+}
+
 // ---- end of refill: clear the dead flags, persist widths, advance the step ----------------
 __global__ void __launch_bounds__(256) end_walk_kernel(EngineState *S, const long long *__restrict__ dead_list,
                                                        unsigned char *is_dead, int d, int tuning_cycles) {
@@ -335,6 +566,7 @@ struct gl_ns {
     bool initialized, pending_refill, finalized;
     // optional CUDA-event timing of the walker / select launches (bench roofline)
     bool prof;
+    bool force_multipass;                         // tests: exercise the multi-launch select path
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -374,6 +606,7 @@ static int check_config(const gl_ns_config *cfg, int d) {
                GL_MAX_TUNING_CYCLES);
     GL_REQUIRE(cfg->proposal == GL_PROPOSAL_UNIFORM || cfg->proposal == GL_PROPOSAL_NORMAL, "unknown proposal");
     GL_REQUIRE(cfg->dead_capacity >= 1, "dead_capacity must be >= 1");
+    GL_REQUIRE(cfg->walker_lanes >= 0 && cfg->walker_lanes <= 32, "walker_lanes outside [0, 32]");
     GL_REQUIRE(cfg->row_offset == 0 && cfg->global_population == cfg->population_size,
                "sharded engines are driven through the multi-GPU host loop (not yet in this build)");
     return GL_OK;
@@ -398,6 +631,7 @@ static WalkParams walk_params(const gl_ns *ns) {
     P.tuning_cycles = ns->cfg.tuning_cycles;
     P.proposal = ns->cfg.proposal;
     P.k_max = ns->cfg.batch_k;
+    P.lanes = ns->cfg.walker_lanes;
     return P;
 }
 
@@ -419,21 +653,39 @@ static void prof_mark(gl_ns *ns, std::vector<cudaEvent_t> &v, cudaStream_t st) {
 
 static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
     const long long N = ns->cfg.population_size;
-    begin_kernel<<<1, 1, 0, st>>>(ns->S, k_req, n_target, N);
-    prof_mark(ns, ns->ev_sel, st);
-    int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
-    if (rc) return rc;
-    prof_mark(ns, ns->ev_sel, st);
-    ns->prof_sel_launches += SEL_PASSES + 2;
-    ns->h_launches += 1 + SEL_PASSES + 2 + 2;     // begin + select + record + accumulate
     const double n_global = (double)ns->cfg.global_population;
-    record_kernel<<<blocks_for((long long)k_req * ns->d, 256, 8), 256, 0, st>>>(
-        ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
-        ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
-        ns->buf.dead_step);
-    accumulate_kernel<<<1, 1024, 0, st>>>(ns->S, ns->dead_list, ns->buf.logl, n_global, n_target,
-                                          ns->cfg.dead_capacity);
-    GL_CHECK_LAUNCH();
+    if (N <= KILL_SMALL_MAX_N && !ns->force_multipass) {
+        const int smem = (int)(sizeof(unsigned long long) * N);
+        static thread_local int configured = 0;
+        if (smem > 40 * 1024 && smem > configured) {
+            GL_CUDA(cudaFuncSetAttribute(kill_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        prof_mark(ns, ns->ev_sel, st);
+        kill_small_kernel<<<1, KILL_SMALL_THREADS, smem, st>>>(
+            ns->S, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
+            ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl,
+            ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+        GL_CHECK_LAUNCH();
+        prof_mark(ns, ns->ev_sel, st);
+        ns->prof_sel_launches += 1;
+        ns->h_launches += 1;
+    } else {
+        begin_kernel<<<1, 1, 0, st>>>(ns->S, k_req, n_target, N);
+        prof_mark(ns, ns->ev_sel, st);
+        int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
+        if (rc) return rc;
+        prof_mark(ns, ns->ev_sel, st);
+        ns->prof_sel_launches += SEL_PASSES + 2;
+        ns->h_launches += 1 + SEL_PASSES + 2 + 2;     // begin + select + record + accumulate
+        record_kernel<<<blocks_for((long long)k_req * ns->d, 256, 8), 256, 0, st>>>(
+            ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
+            ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
+            ns->buf.dead_step);
+        accumulate_kernel<<<1, 1024, 0, st>>>(ns->S, ns->dead_list, ns->buf.logl, n_global, n_target,
+                                              ns->cfg.dead_capacity);
+        GL_CHECK_LAUNCH();
+    }
     long long k = n_target - ns->h_n_dead;
     if (k > k_req) k = k_req;
     if (k > N - 1) k = N - 1;
@@ -514,6 +766,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->h_step = ns->h_k_last = 0;
     ns->initialized = ns->pending_refill = ns->finalized = false;
     ns->prof = false;
+    ns->force_multipass = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
@@ -690,6 +943,12 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
 }  // extern "C"
 
 extern "C" {
+
+int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    ns->force_multipass = enable != 0;
+    return GL_OK;
+}
 
 int gl_ns_profile_enable(gl_ns *ns, int32_t enable) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");

@@ -39,11 +39,13 @@ struct WalkParams {                  // by-value kernel parameter
     long long row_offset;
     uint64_t seed;
     int d, iterations, burn_in, tuning_cycles, proposal, k_max;
+    int lanes;                       // lanes per walker (0 = choose from k_max)
 };
 
 // walker.cu
 int walk_launch(const WalkParams &P, const ModelDev &M, cudaStream_t st);
-int walker_smem_bytes(int d, int threads);
+int walker_smem_bytes(int d, int nc, int G);
+int walker_group_size(int k_max, int requested);
 
 // loglike.cu / priors.cu
 int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, double *logl_dev, cudaStream_t st);

@@ -38,4 +38,29 @@ __device__ __forceinline__ double prior_ppf(int kind, double p0, double p1, doub
     }
 }
 
+// Metropolis prior test of one component move (samplers.py:105-107,110): returns
+// (u < prior(new)/prior(cur)) with the ratio simplified algebraically per family, so that no
+// division or exp is spent where the answer is already decided:
+//   uniform     ratio in {1, 0, inf, nan}            ->  inside(new)
+//   norm        exp(-0.5*(zn^2 - zc^2))              ->  true when zn^2 <= zc^2 (ratio >= 1 > u)
+//   loguniform  cur/new inside the support            ->  inside(new) && (!inside(cur) || u < cur/new)
+// inside(x) := 0 <= x - p0 <= p1 (uniform) / p0 <= x <= p1 (loguniform); NaN is outside.
+// Same forms as oracle/priors.py::accept_prior.
+__device__ __forceinline__ bool prior_accept(int kind, double p0, double p1, double cur, double nw, double u) {
+    if (kind == GL_PRIOR_UNIFORM) {
+        const double t = nw - p0;
+        return t >= 0.0 && t <= p1;
+    } else if (kind == GL_PRIOR_NORM) {
+        const double zn = (nw - p0) / p1, zc = (cur - p0) / p1;
+        const double a = zn * zn, b = zc * zc;
+        if (a <= b) return true;
+        return u < exp(-0.5 * (a - b));
+    } else {
+        const bool in_n = nw >= p0 && nw <= p1;
+        if (!in_n) return false;
+        const bool in_c = cur >= p0 && cur <= p1;
+        return !in_c || u < cur / nw;
+    }
+}
+
 }  // namespace gl

@@ -20,7 +20,7 @@ class DeviceEngine(object):
     """One device-resident NS run: live set, dead-point log, accumulators, widths."""
 
     def __init__(self, prior_table, model_handle, population_size, batch_k, n_deaths_capacity, iterations=100,
-                 burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None):
+                 burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None, walker_lanes=0):
         torch = _torch()
         self.lib = _lib.load()
         self.d = len(prior_table)
@@ -29,7 +29,7 @@ class DeviceEngine(object):
         cap = int(n_deaths_capacity) + self.N
         self.cfg = _lib.gl_ns_config(population_size=self.N, batch_k=int(batch_k), iterations=int(iterations),
                                      burn_in=int(burn_in), tuning_cycles=int(tuning_cycles),
-                                     proposal=int(proposal), reserved=0, seed=int(seed) & (2 ** 64 - 1),
+                                     proposal=int(proposal), walker_lanes=int(walker_lanes), seed=int(seed) & (2 ** 64 - 1),
                                      dead_capacity=cap, row_offset=0, global_population=self.N)
         ws = self.lib.gl_ns_workspace_bytes(ctypes.byref(self.cfg), self.d)
         if ws < 0:
@@ -90,6 +90,9 @@ class DeviceEngine(object):
 
     def finalize(self):
         _lib.check(self.lib.gl_ns_finalize(self._h, self._stream()))
+
+    def force_multipass_select(self, enable=True):
+        _lib.check(self.lib.gl_ns_force_multipass_select(self._h, 1 if enable else 0))
 
     def profile_enable(self, enable=True):
         _lib.check(self.lib.gl_ns_profile_enable(self._h, 1 if enable else 0))

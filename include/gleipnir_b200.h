@@ -130,7 +130,7 @@ typedef struct gl_ns_config {
     int32_t burn_in;         /* samplers.py:42                                               */
     int32_t tuning_cycles;   /* samplers.py:43 (each cycle = 20 sweeps)                      */
     int32_t proposal;        /* samplers.py:44  gl_proposal_kind                             */
-    int32_t reserved;
+    int32_t walker_lanes;    /* lanes cooperating on one walker (speculative prefetch): 0 = auto, else 1..32 */
     uint64_t seed;           /* Philox key                                                   */
     int64_t dead_capacity;   /* rows the dead buffers can hold (>= n_deaths + N)             */
     int64_t row_offset;      /* global index of local row 0 (multi-GPU shard), else 0        */
@@ -200,6 +200,11 @@ GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 
 /* Copy the device state to the host (synchronises `stream`). */
 GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
+
+/* Populations whose ordering keys fit in shared memory (N <= 24576) use a single-CTA fused
+ * kill kernel; this switch forces the general multi-launch selection path (used by tests so
+ * that both paths are checked against each other and the oracle). */
+GL_API int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable);
 
 /* Optional CUDA-event timing of the two kernel groups that dominate a step, recorded on the
  * launching stream: walker launches (tuning_cycles+1 per step) and selection launches (8 per

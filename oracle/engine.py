@@ -182,8 +182,8 @@ class Engine(object):
     # -- a11/a12/a16-a18: refill the dead slots ------------------------------------------
     def _propose(self, r, cur, w):
         if self.proposal == "normal":
-            return pr.ndtri(r) * w + cur
-        return r * w + (cur - w / 2.0)
+            return pr.ndtri(r) * w + cur              # samplers.py:100
+        return r * w + (cur + (-0.5 * w))             # samplers.py:102: ppf(r, loc=cur-w/2, scale=w)
 
     def _sweeps(self, slots, cur, cur_l, widths, t0, n_sweeps, count):
         """n_sweeps component-wise sweeps for all walkers at once (vectorised over walkers)."""
@@ -195,11 +195,11 @@ class Engine(object):
                     r, u = px.uniforms(self.seed, slots, self.step, t * d + j, px.GL_TAG_MOVE)
                     xj = cur[:, j]
                     nj = self._propose(r, xj, widths[j])
-                    ratio = pr.pdf(kind, p0, p1, nj) / pr.pdf(kind, p0, p1, xj)
+                    okp = pr.accept_prior(kind, p0, p1, xj, nj, u)
                     trial = cur.copy()
                     trial[:, j] = nj
                     tl = self.model(trial)
-                    ok = (u < ratio) & (tl > self.lstar)
+                    ok = okp & (tl > self.lstar)
                     cur[ok, j] = nj[ok]
                     cur_l[ok] = tl[ok]
                     if count:

@@ -55,6 +55,28 @@ def ppf(kind, p0, p1, u):
     raise ValueError(kind)
 
 
+def accept_prior(kind, p0, p1, cur, new, u):
+    """(u < prior(new)/prior(cur)) of samplers.py:105-107,110 with the ratio simplified per
+    family (same forms as csrc/priors.cuh::prior_accept):
+      uniform: the ratio is 1, 0, inf or nan -> accept iff new is inside the support;
+      norm: exp(-0.5*(zn^2 - zc^2));  loguniform: cur/new inside the support."""
+    cur = np.asarray(cur, dtype=np.float64)
+    new = np.asarray(new, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        if kind == GL_PRIOR_UNIFORM:
+            t = new - p0
+            return (t >= 0.0) & (t <= p1)
+        if kind == GL_PRIOR_NORM:
+            zn, zc = (new - p0) / p1, (cur - p0) / p1
+            a, b = zn * zn, zc * zc
+            return (a <= b) | (u < np.exp(-0.5 * (a - b)))
+        if kind == GL_PRIOR_LOGUNIFORM:
+            in_n = (new >= p0) & (new <= p1)
+            in_c = (cur >= p0) & (cur <= p1)
+            return in_n & (~in_c | (u < cur / new))
+    raise ValueError(kind)
+
+
 def parse_scipy_frozen(prior):
     """scipy frozen distribution -> (kind, p0, p1); mirrors the product-side parser."""
     name = prior.dist.name

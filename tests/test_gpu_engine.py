@@ -17,13 +17,17 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-def _engine(table, dev_like, N, k, cap, **kw):
+def _engine(table, dev_like, N, k, cap, multipass=False, **kw):
     from gleipnir_b200.engine import DeviceEngine
-    return DeviceEngine(table, dev_like.device_model(), N, k, cap, **kw)
+    eng = DeviceEngine(table, dev_like.device_model(), N, k, cap, **kw)
+    if multipass:        # general multi-launch selection instead of the fused single-CTA kill
+        eng.force_multipass_select(True)
+    return eng
 
 
+@pytest.mark.parametrize("multipass", [False, True], ids=["fused", "multipass"])
 @pytest.mark.parametrize("name", ["plain", "ties", "neginf", "nan", "N1000"])
-def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name):
+def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name, multipass):
     """Identical initial logL + identical replacement stream -> identical dead rows, order and
     slots (bit-exact); weights/Z/H/information to rounding (SURVEY 8c parity definition 1)."""
     from gleipnir_b200 import likelihoods as lk
@@ -31,7 +35,8 @@ def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name):
     live0, logl0 = g[name + "/live0"], g[name + "/logl0"]
     N, d = live0.shape
     n_iter = int(g[name + "/n_iter"])
-    eng = _engine([(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d, lk.IIDGaussianLogLikelihood(d), N, 1, n_iter)
+    eng = _engine([(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d, lk.IIDGaussianLogLikelihood(d), N, 1, n_iter,
+                  multipass=multipass)
     eng.init(live0, logl0)
     rx, rl = g[name + "/repl_x"], g[name + "/repl_l"]
     for i in range(n_iter):
@@ -55,8 +60,9 @@ def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name):
         np.testing.assert_allclose(np.sqrt(st.information / N), g[name + "/logZ_err"], rtol=1e-11)
 
 
+@pytest.mark.parametrize("multipass", [False, True], ids=["fused", "multipass"])
 @pytest.mark.parametrize("k", [1, 7, 32])
-def test_outer_loop_replay_batched_matches_oracle(cuda, golden_dir, k):
+def test_outer_loop_replay_batched_matches_oracle(cuda, golden_dir, k, multipass):
     from gleipnir_b200 import likelihoods as lk
     g = np.load(os.path.join(golden_dir, "ref_replay.npz"))
     live0, logl0 = g["N1000/live0"], g["N1000/logl0"]
@@ -66,7 +72,8 @@ def test_outer_loop_replay_batched_matches_oracle(cuda, golden_dir, k):
     o = Engine([(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d, None, N, batch_k=k)
     o.init(live0, logl0)
     want = o.continue_run(n_iter, (rx, rl))
-    eng = _engine([(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d, lk.IIDGaussianLogLikelihood(d), N, k, n_iter)
+    eng = _engine([(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d, lk.IIDGaussianLogLikelihood(d), N, k, n_iter,
+                  multipass=multipass)
     eng.init(live0, logl0)
     pos, done = 0, 0
     while done < n_iter:
@@ -108,8 +115,9 @@ def _mk(kind, d):
     return lk.Mixture1DLogLikelihood(), Model("mixture1d", 1, positions=[0.1, 0.2, 0.5, 0.55, 0.9, 1.1], width=0.01)
 
 
+@pytest.mark.parametrize("multipass", [False, True], ids=["fused", "multipass"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_whole_run_matches_oracle_engine(cuda, case):
+def test_whole_run_matches_oracle_engine(cuda, case, multipass):
     """Same Philox counters on both sides -> the CUDA engine and the CPU restatement must
     produce the same run: dead slots bit-identical, rows and logL within 1e-12
     (SURVEY 8c parity definition 2)."""
@@ -120,7 +128,7 @@ def test_whole_run_matches_oracle_engine(cuda, case):
     want = o.run(n_deaths)
     dkw = dict(skw)
     dkw["proposal"] = 1 if dkw.get("proposal") == "normal" else 0
-    eng = _engine(table, dev_like, N, k, n_deaths, seed=seed, **dkw)
+    eng = _engine(table, dev_like, N, k, n_deaths, multipass=multipass, seed=seed, **dkw)
     eng.init()
     eng.advance(n_deaths)
     eng.finalize()
@@ -144,7 +152,7 @@ def test_run_host_entry_point_matches_device_api(cuda):
     table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d
     like = lk.IIDGaussianLogLikelihood(d)
     cfg = L.gl_ns_config(population_size=N, batch_k=k, iterations=10, burn_in=0, tuning_cycles=1, proposal=0,
-                         reserved=0, seed=77, dead_capacity=n_deaths + N, row_offset=0, global_population=N)
+                         walker_lanes=0, seed=77, dead_capacity=n_deaths + N, row_offset=0, global_population=N)
     dead = np.zeros((n_deaths + N, d + 2))
     st = L.gl_ns_state()
     L.check(lib.gl_ns_run_host(ctypes.byref(cfg), L.prior_array(table), d, like.device_model(), n_deaths,
@@ -222,3 +230,53 @@ def test_reference_test_suite_flow(cuda):
     assert NS.best_fit_likelihood().shape == (ndim,)
     with pytest.warns(UserWarning):
         NS.evidence = 1.0
+
+
+@pytest.mark.parametrize("kind,d", [("egg", 2), ("iid", 5), ("dense", 12)])
+def test_speculative_lanes_are_bit_identical(cuda, kind, d):
+    """Speculative prefetch (G lanes per walker) must retire exactly the sequential chain:
+    every group size gives the same run, bit for bit."""
+    from gleipnir_b200 import likelihoods as lk
+    from oracle import likelihoods as olk
+    if kind == "dense":
+        mu, P, ln = olk.make_c3_dense_gaussian(d)
+        like = lk.DenseGaussianLogLikelihood(mu, P, ln)
+        table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d
+    else:
+        like, _ = _mk(kind, d)
+        table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d if kind == "egg" else [(pr.GL_PRIOR_NORM, 0.0, 3.0)] * d
+    N, k, n_deaths = 300, 30, 600
+    ref = None
+    for lanes in (1, 2, 4, 8, 16, 32, 0):
+        eng = _engine(table, like, N, k, n_deaths, seed=5, iterations=7, burn_in=1, tuning_cycles=2,
+                      walker_lanes=lanes)
+        eng.init()
+        eng.advance(n_deaths)
+        eng.finalize()
+        tab, idx, _ = eng.dead_table()
+        st = eng.state()
+        cur = (tab, idx, st.log_z, st.information, np.array(st.widths[:d]))
+        if ref is None:
+            ref = cur
+        else:
+            assert np.array_equal(cur[0], ref[0]) and np.array_equal(cur[1], ref[1]), lanes
+            assert cur[2] == ref[2] and cur[3] == ref[3] and np.array_equal(cur[4], ref[4]), lanes
+
+
+def test_fused_and_multipass_kill_agree_at_the_size_limit(cuda):
+    """N = 24576 is the largest population of the fused single-CTA kill; N = 24577 takes the
+    multi-launch path.  Both must agree with each other on the same inputs."""
+    from gleipnir_b200 import likelihoods as lk
+    table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * 2
+    like = lk.EggCartonLogLikelihood(2)
+    N, k, n_deaths = 24576, 3000, 9000
+    out = []
+    for mp in (False, True):
+        eng = _engine(table, like, N, k, n_deaths, multipass=mp, seed=3, iterations=5, tuning_cycles=1)
+        eng.init(); eng.advance(n_deaths); eng.finalize()
+        tab, idx, _ = eng.dead_table()
+        st = eng.state()
+        out.append((tab, idx, st.log_z, st.information, st.n_launches))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+    assert out[0][4] < out[1][4]          # the fused path really launched fewer kernels
