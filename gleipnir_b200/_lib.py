@@ -66,6 +66,7 @@ _SIGNATURES = {
     "gl_model_create_eggcarton": (c_int, [c_int32, POINTER(_P)]),
     "gl_model_create_mixture1d": (c_int, [POINTER(c_double), c_int32, c_double, POINTER(_P)]),
     "gl_model_create_dense_gaussian": (c_int, [c_int32, POINTER(c_double), POINTER(c_double), c_double, POINTER(_P)]),
+    "gl_model_create_external": (c_int, [c_int32, _P, _P, _P, c_int64, POINTER(_P)]),
     "gl_model_dim": (c_int, [_P]),
     "gl_model_kind_of": (c_int, [_P]),
     "gl_model_destroy": (c_int, [_P]),

@@ -5,14 +5,30 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <stdarg.h>
 
 #include "../../include/gleipnir_b200.h"
 
 namespace gl {
 
 // ---- error plumbing (thread-local last-error string behind gl_last_error) --------
-void set_error(const char *fmt, ...);
-int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+// Header-only so that code-generated plugin libraries (ODE networks) are self-contained; each
+// shared object keeps its own buffer (the core library reads a plugin's through its
+// gl_plugin_last_error entry point).
+inline char *error_buffer() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+inline void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+}
+inline int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return GL_ECUDA;
+}
 
 #define GL_CUDA(call)                                                       \
     do {                                                                    \
@@ -34,7 +50,15 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                                                                   \
     } while (0)
 
-int sm_count();   // cached; 148 on B200
+inline int sm_count() {   // cached; 148 on B200
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached = n;
+    return n;
+}
 
 // ---- ordering key: np.argmin order (NaN first, -0.0 == +0.0), ascending ----------
 __host__ __device__ __forceinline__ unsigned long long sort_key(double x) {

@@ -44,8 +44,6 @@ struct WalkParams {                  // by-value kernel parameter
 
 // walker.cu
 int walk_launch(const WalkParams &P, const ModelDev &M, cudaStream_t st);
-int walker_smem_bytes(int d, int nc, int G);
-int walker_group_size(int k_max, int requested);
 
 // loglike.cu / priors.cu
 int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, double *logl_dev, cudaStream_t st);

@@ -1,40 +1,11 @@
 // Library plumbing: last-error string, device info.
-#include <stdarg.h>
 #include "common.cuh"
-
-namespace gl {
-
-static thread_local char g_err[512] = "";
-
-void set_error(const char *fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-}
-
-int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
-    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
-    return GL_ECUDA;
-}
-
-int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
-    return n;
-}
-
-}  // namespace gl
 
 extern "C" {
 
 int gl_abi_version(void) { return GL_ABI_VERSION; }
 
-const char *gl_last_error(void) { return gl::g_err; }
+const char *gl_last_error(void) { return gl::error_buffer(); }
 
 int gl_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;

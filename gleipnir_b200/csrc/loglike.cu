@@ -2,20 +2,9 @@
 // (replaces the N scalar `loglikelihood(row)` calls of nested_sampling.py:108).
 #include "common.cuh"
 #include "likelihoods.cuh"
+#include "loglike.cuh"
 
 namespace gl {
-
-// One thread per parameter vector; rows are read straight from global memory (for the
-// small-d analytic models a row is 16-40 B, the whole array streams through L1 once).
-template <class Like>
-__global__ void __launch_bounds__(256) loglike_rows_kernel(ModelDev M, const double *__restrict__ x, long long n,
-                                                           double *__restrict__ out) {
-    const Like like(M);
-    const int d = M.d;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        out[i] = like.eval(x + i * d, 1);
-}
 
 struct EvalLauncher {
     const gl_model *m;
@@ -25,12 +14,7 @@ struct EvalLauncher {
     cudaStream_t st;
     template <class Like>
     int operator()() {
-        long long blocks = (n + 255) / 256;
-        long long cap = (long long)sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        loglike_rows_kernel<Like><<<(int)blocks, 256, 0, st>>>(m->dev, x, n, out);
-        GL_CHECK_LAUNCH();
-        return GL_OK;
+        return loglike_rows_launch<Like>(m->dev, x, n, out, st);
     }
 };
 
@@ -38,6 +22,10 @@ int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, dou
     GL_REQUIRE(m != nullptr, "model is NULL");
     if (n <= 0) return GL_OK;
     GL_REQUIRE(x_dev != nullptr && logl_dev != nullptr, "NULL device pointer");
+    if (m->dev.kind == GL_MODEL_EXTERNAL) {
+        GL_REQUIRE(m->dev.ext_eval != nullptr, "external model without an eval entry point");
+        return m->dev.ext_eval(&m->dev, x_dev, n, logl_dev, (void *)st);
+    }
     EvalLauncher L{m, x_dev, n, logl_dev, st};
     return dispatch_model(m->dev.kind, L);
 }
@@ -111,6 +99,30 @@ int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const doubl
     m->dev.s0 = log_norm;
     m->dev.aux0 = m->aux_alloc;
     m->dev.aux1 = m->aux_alloc + nd;
+    return GL_OK;
+}
+
+int gl_model_create_external(int32_t d, void *walk_fn, void *eval_fn, const void *blob_host, int64_t blob_bytes,
+                             gl_model **out) {
+    GL_REQUIRE(walk_fn != nullptr && eval_fn != nullptr, "plugin entry points are NULL");
+    GL_REQUIRE(blob_bytes >= 0 && (blob_bytes == 0 || blob_host != nullptr), "bad blob");
+    int rc = gl::new_model(GL_MODEL_EXTERNAL, d, out);
+    if (rc) return rc;
+    gl_model *m = *out;
+    if (blob_bytes > 0) {
+        cudaError_t e = cudaMalloc(&m->aux_alloc, (size_t)blob_bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(m->aux_alloc, blob_host, (size_t)blob_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(m->aux_alloc);
+            delete m;
+            *out = nullptr;
+            return gl::cuda_fail(e, "external model blob upload", __FILE__, __LINE__);
+        }
+    }
+    m->dev.aux0 = m->aux_alloc;
+    m->dev.n_aux = (int32_t)(blob_bytes / 8);
+    m->dev.ext_walk = (int (*)(const void *, const void *, void *))walk_fn;
+    m->dev.ext_eval = (int (*)(const void *, const double *, long long, double *, void *))eval_fn;
     return GL_OK;
 }
 

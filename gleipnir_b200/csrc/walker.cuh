@@ -1,0 +1,245 @@
+// Constrained component-wise Metropolis walkers: the B200 form of
+// MetropolisComponentWiseHardNSRejection.__call__ (samplers.py:56-152) applied to a whole
+// batch of dead slots at once.  Each walker replaces one dead slot:
+//   * seed  = uniformly chosen survivor, int(U*N) redrawn while it hits a dead slot
+//             (nested_sampling.py:147-149);
+//   * move  = the reference's *tuning-loop* move (samplers.py:95-114): propose component j
+//             from a symmetric uniform/normal window of width w_j, accept iff
+//             u < prior_j(new)/prior_j(cur) AND logL(new) > L*  (hard NS wall);
+//   * phases: `tuning_cycles` launches of 20 sweeps whose positions are discarded and whose
+//             pooled acceptance adapts w (see phase_width), then one launch of
+//             iterations+burn_in sweeps from the seed again whose end point is written
+//             into the dead slot (samplers.py:124-152 without quirk Q1).
+//
+// Speculative prefetch.  A Metropolis chain is one dependent sequence of trial moves, so a
+// walker-per-thread kernel is bound by the latency of that chain (r01 baseline: 423 warp
+// instructions and ~2500 cycles per trial move with one warp per SM sub-partition).  Here a
+// GROUP of G lanes (G = 1..32, chosen on the host from the batch size) serves one walker:
+// lane i evaluates trial move m+i from the CURRENT state, which is exactly the state move
+// m+i would see if moves m..m+i-1 are all rejected.  A ballot finds the first accepting
+// lane f; moves m..m+f-1 were rejections, move m+f is committed, and the window restarts
+// at m+f+1.  Randomness is Philox4x32-10 keyed by (global slot, step, move index) -- one
+// block yields the proposal uniform r and the acceptance uniform u of a trial move -- so the
+// retired sequence of moves, decisions and values is IDENTICAL to the sequential chain
+// for every G; speculation only shortens the critical path (~1/p_accept moves per round).
+//
+// State: the walker's point x[d], the likelihood cache (see likelihoods.cuh) and logL live
+// in shared memory, column-per-walker (conflict-free; lanes of a group broadcast-read).
+// Bound: FP64 pipe / dependent-chain latency; HBM traffic is 8(2d+1) B per replacement.
+#pragma once
+#include "engine.cuh"
+#include "philox.cuh"
+
+namespace gl {
+
+constexpr int WALK_THREADS = 128;
+
+// moves pre-generated per refill of a walker's random-number ring
+__host__ __device__ inline int walker_chunk(int G) { return 4 * G > 8 ? 4 * G : 8; }
+
+// FULL = true: G == 32, one group per warp, every intra-group primitive uses the constant full
+// mask (no mask-validation code); FULL = false: runtime power-of-two G < 32.
+template <class Like, bool FULL>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkParams P, ModelDev M, int phase, int lgG) {
+    extern __shared__ double sm[];
+    EngineState *S = P.S;
+    if (!S->do_walk) return;                       // grid-uniform
+    const int k = S->k_cur;
+    const int d = P.d;
+    const int G = FULL ? 32 : (1 << lgG);
+    const int WPB = WALK_THREADS >> lgG;           // walkers per block
+    if (blockIdx.x * WPB >= k) return;             // block-uniform
+    const int nc = Like::cache_size(d);
+    const int CH = walker_chunk(G);
+    // shared layout: x[d][WPB] | cache[nc][WPB] | step[WPB][CH] | u[WPB][CH] | width[d] | p0[d] | p1[d]
+    //                | kind[d] | acc[d]
+    double *xs = sm;
+    double *cs = xs + (size_t)d * WPB;
+    double *sbuf = cs + (size_t)nc * WPB;
+    double *ubuf = sbuf + (size_t)WPB * CH;
+    double *wj = ubuf + (size_t)WPB * CH;
+    double *p0s = wj + d;
+    double *p1s = p0s + d;
+    int *kinds = reinterpret_cast<int *>(p1s + d);
+    unsigned int *acc = reinterpret_cast<unsigned int *>(kinds + d);
+
+    const int tid = threadIdx.x;
+    const bool tuning = phase < P.tuning_cycles;
+    for (int j = tid; j < d; j += WALK_THREADS) {
+        wj[j] = phase_width(S, j, phase, k);
+        p0s[j] = P.priors->p0[j];
+        p1s[j] = P.priors->p1[j];
+        kinds[j] = P.priors->kind[j];
+        acc[j] = 0u;
+    }
+    __syncthreads();
+
+    const int wl = tid >> lgG;                     // walker within block
+    const int lane = tid & (G - 1);                // lane within group
+    const int w = blockIdx.x * WPB + wl;           // walker within batch
+    const bool active = w < k;                     // group-uniform
+    const unsigned gbase = FULL ? 0u : (unsigned)((tid & 31) & ~(G - 1));
+    const unsigned gmask = FULL ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    double *x = xs + wl;
+    double *c = cs + wl;
+    double *sb = sbuf + (size_t)wl * CH;
+    double *ub = ubuf + (size_t)wl * CH;
+    const Like like(M);
+    const double lstar = S->lstar;
+    const uint32_t step = (uint32_t)S->step;
+    // n % d == n - umulhi(n, dmagic)*d for n < 2^32/d (dmagic = ceil(2^32/d); d = 1 -> 0 -> n - 0*1 handled below)
+    const uint32_t dmagic = d > 1 ? 0xFFFFFFFFu / (uint32_t)d + 1u : 0u;
+
+    if (active) {
+        const long long slot = P.dead_list[w];
+        const uint32_t g = (uint32_t)(slot + P.row_offset);
+        // ---- start point ------------------------------------------------------------------
+        if (phase == 0 || !tuning) {
+            long long pick = 0;
+            if (lane == 0) {
+                for (uint32_t a = 0;; ++a) {       // survivor pick, redraw while dead
+                    const U2 u = philox_uniforms(P.seed, g, step, a, GL_TAG_PICK);
+                    pick = (long long)(u.a * (double)P.N);
+                    if (pick >= P.N) pick = P.N - 1;
+                    if (!P.is_dead[pick]) break;
+                }
+            }
+            pick = __shfl_sync(gmask, pick, gbase);
+            const double *src = P.live + pick * d;
+            for (int j = lane; j < d; j += G) x[j * WPB] = src[j];
+        } else {
+            const double *src = P.scratch_x + (size_t)w * d;
+            for (int j = lane; j < d; j += G) x[j * WPB] = src[j];
+        }
+        __syncwarp(gmask);
+        double L = like.init(x, c, WPB, lane, G, gmask);
+
+        // ---- speculative rounds --------------------------------------------------------------
+        const int n_moves = (tuning ? 20 : P.iterations + P.burn_in) * d;
+        const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * d);
+        const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
+        int m = 0, base = -CH;                     // ring holds moves [base, base+CH)
+        while (m < n_moves) {                      // group-uniform
+            if (m + G > base + CH) {
+                // refill: everything about moves [m, m+CH) that does not depend on the walker's
+                // state -- Philox block, proposal step r*w (or ndtri(r)*w), acceptance uniform.
+                // Independent per move: the CH/G Philox chains of a lane overlap (ILP).
+                base = m;
+                __syncwarp(gmask);
+                for (int q = lane; q < CH; q += G) {
+                    const int mv = base + q;
+                    if (mv < n_moves) {
+                        const uint32_t jj = d > 1 ? (uint32_t)mv - __umulhi((uint32_t)mv, dmagic) * (uint32_t)d : 0u;
+                        const U2 ru = philox_uniforms(P.seed, g, step, c2_base + (uint32_t)mv, GL_TAG_MOVE);
+                        sb[q] = __dmul_rn(normal ? normcdfinv(ru.a) : ru.a, wj[jj]);
+                        ub[q] = ru.b;
+                    }
+                }
+                __syncwarp(gmask);
+            }
+            const int mine = m + lane;
+            bool ok = false;
+            int j = 0;
+            double nj = 0.0, Lt = 0.0, cnew = 0.0;
+            if (mine < n_moves) {
+                j = d > 1 ? (int)((uint32_t)mine - __umulhi((uint32_t)mine, dmagic) * (uint32_t)d) : 0;
+                const double xj = x[j * WPB];
+                // uniform: r*w + (x - w/2)   normal: ndtri(r)*w + x     (samplers.py:100,102)
+                const double loc = normal ? xj : __dadd_rn(xj, -0.5 * wj[j]);
+                nj = __dadd_rn(sb[mine - base], loc);
+                if (prior_accept(kinds[j], p0s[j], p1s[j], xj, nj, ub[mine - base])) {
+                    Lt = like.trial(x, c, WPB, j, nj, cnew);
+                    ok = Lt > lstar;
+                }
+            }
+            const unsigned bal = __ballot_sync(gmask, ok) & gmask;
+            if (bal == 0u) {
+                m += G;
+                continue;
+            }
+            const int f = __ffs(bal) - 1;          // absolute lane of the first accept
+            // broadcast the accepted move to the group and commit cooperatively
+            j = __shfl_sync(gmask, j, f);
+            nj = __shfl_sync(gmask, nj, f);
+            Lt = __shfl_sync(gmask, Lt, f);
+            cnew = __shfl_sync(gmask, cnew, f);
+            like.commit(x, c, WPB, j, nj, cnew, lane, G, gmask);
+            L = Lt;
+            if (tuning && lane == 0) atomicAdd(&acc[j], 1u);
+            __syncwarp(gmask);
+            m += (f - (int)gbase) + 1;
+        }
+
+        // ---- write back ----------------------------------------------------------------------
+        if (tuning) {
+            if (phase + 1 < P.tuning_cycles) {
+                double *dst = P.scratch_x + (size_t)w * d;
+                for (int j = lane; j < d; j += G) dst[j] = x[j * WPB];
+            }
+        } else {
+            L = like.refresh(x, c, WPB, lane, G, gmask, L);
+            double *dst = P.live + slot * d;
+            for (int j = lane; j < d; j += G) dst[j] = x[j * WPB];
+            if (lane == 0) P.logl[slot] = L;
+        }
+    }
+    if (tuning) {
+        __syncthreads();
+        for (int j = tid; j < d; j += WALK_THREADS)
+            if (acc[j]) atomicAdd(&S->acc[phase][j], acc[j]);
+    }
+}
+
+inline int walker_smem_bytes(int d, int nc, int G) {
+    const int WPB = WALK_THREADS / G;
+    return (int)(sizeof(double) * ((size_t)(d + nc) * WPB + 2 * (size_t)WPB * walker_chunk(G) + 3 * (size_t)d) +
+                 2 * sizeof(int) * d + 16);
+}
+
+// lanes per walker: the largest power of two that keeps the whole batch resident
+// (k_max * G threads <= one wave at 1024 threads per SM), capped at 32.
+inline int walker_group_size(int k_max, int requested) {
+    if (requested >= 1) {
+        int g = 1;
+        while (g * 2 <= requested && g < 32) g *= 2;
+        return g;
+    }
+    const long long cap = (long long)sm_count() * 1024;
+    int g = 32;
+    while (g > 1 && (long long)k_max * g > cap) g >>= 1;
+    return g;
+}
+
+struct WalkLauncher {
+    const WalkParams &P;
+    const ModelDev &M;
+    cudaStream_t st;
+    template <class Like>
+    int operator()() {
+        int G = walker_group_size(P.k_max, P.lanes);
+        int smem = walker_smem_bytes(P.d, Like::cache_size(P.d), G);
+        while (smem > 200 * 1024 && G < 32) {      // very large d: fewer walkers per block
+            G *= 2;
+            smem = walker_smem_bytes(P.d, Like::cache_size(P.d), G);
+        }
+        GL_REQUIRE(smem <= 227 * 1024, "walker state does not fit in shared memory (d=%d)", P.d);
+        static thread_local int configured_smem = 0;
+        if (smem > 48 * 1024 && smem > configured_smem) {
+            GL_CUDA(cudaFuncSetAttribute(walk_kernel<Like, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            GL_CUDA(cudaFuncSetAttribute(walk_kernel<Like, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured_smem = smem;
+        }
+        const int WPB = WALK_THREADS / G;
+        const int blocks = (P.k_max + WPB - 1) / WPB;
+        int lgG = 0;
+        while ((1 << lgG) < G) ++lgG;
+        for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
+            if (G == 32) walk_kernel<Like, true><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+            else walk_kernel<Like, false><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+        }
+        GL_CHECK_LAUNCH();
+        return GL_OK;
+    }
+};
+
+}  // namespace gl

@@ -91,7 +91,8 @@ enum gl_model_kind {
     GL_MODEL_IID_GAUSSIAN = 0,  /* tests/test_nested_sampling.py:34-36                */
     GL_MODEL_EGGCARTON = 1,     /* examples/eggcarton/NS_eggcarton.py:25-27          */
     GL_MODEL_MIXTURE1D = 2,     /* examples/1d_multimodal/NS_1d_multimodal.py:20-32  */
-    GL_MODEL_DENSE_GAUSSIAN = 3 /* synthetic C3 (not in reference) */
+    GL_MODEL_DENSE_GAUSSIAN = 3, /* synthetic C3 (not in reference) */
+    GL_MODEL_EXTERNAL = 100      /* code-generated plugin (ODE networks)               */
 };
 
 /* -0.5*sum(((x-mu)/sigma)^2) - d*(0.5*log(2*pi) + log(sigma)) */
@@ -103,6 +104,15 @@ GL_API int gl_model_create_mixture1d(const double *positions_host, int32_t n_pos
 /* -0.5*(x-mu)^T P (x-mu) + log_norm; P row-major [d, d] symmetric. */
 GL_API int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const double *P_host, double log_norm,
                                    gl_model **out);
+/* A code-generated model (PySB-style mass-action ODE network, gleipnir_b200/odegen.py): the
+ * plugin library compiled from the generated source exports gl_plugin_walk_launch /
+ * gl_plugin_eval_launch, which instantiate this library's walker and batch-eval kernel
+ * templates for the network's functor (stiff integrator + fused misfit).  `blob_host` is the
+ * network's data block (nominal parameters, sampled-parameter map, time points, data, sd),
+ * copied to the device.  Replaces the `loglikelihood` closures over ScipyOdeSimulator of
+ * gleipnir/pysb_utilities/nestedsample_it.py:273-339. */
+GL_API int gl_model_create_external(int32_t d, void *walk_fn, void *eval_fn, const void *blob_host,
+                                    int64_t blob_bytes, gl_model **out);
 GL_API int gl_model_dim(const gl_model *m);
 GL_API int gl_model_kind_of(const gl_model *m);
 GL_API int gl_model_destroy(gl_model *m);

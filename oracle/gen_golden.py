@@ -180,9 +180,30 @@ def prior_tables(m):
     np.savez_compressed(os.path.join(OUT, "ref_priors.npz"), **out)
 
 
+def ode_fixtures():
+    """The reference's ODE data files, copied verbatim as fixtures (they are data, not code):
+    model_0_AB_complex_data.npy is the one genuine ScipyOdeSimulator trajectory in the tree
+    (examples/HypSelector/grouped_reactions/run_grouped_reactions_nsclassic.py:10-11,27: model_0 at
+    default parameters, tspan = linspace(0, 5, 20), last 10 points); the dimerization pair is the
+    likelihood input of examples/pysb_dimerization_model/run_NS_dimerization_model.py:22-24."""
+    ref = ref_shim.REFERENCE_ROOT
+    out = {
+        "model_0/AB_complex_last10": np.load(os.path.join(ref, "jupyter_notebooks", "model_0_AB_complex_data.npy")),
+        "model_0/tspan": np.linspace(0, 5, 20),
+        "dimerization/data": np.load(os.path.join(ref, "examples", "pysb_dimerization_model",
+                                                  "dimerization_model_dimer_data.npy")),
+        "dimerization/sd": np.load(os.path.join(ref, "examples", "pysb_dimerization_model",
+                                                "dimerization_model_dimer_sd.npy")),
+        "dimerization/tspan": np.linspace(0, 1, num=51),
+    }
+    np.savez_compressed(os.path.join(OUT, "ref_ode.npz"), **out)
+    print("ode fixtures", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     mods = ref_shim.load_reference()
     full_runs(mods)
     replay_cases(mods)
     prior_tables(mods)
+    ode_fixtures()

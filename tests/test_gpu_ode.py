@@ -1,0 +1,132 @@
+"""GPU parity (ODE likelihoods): the code-generated Rosenbrock kernels against the SciPy
+stand-in oracle (LSODA, rtol=atol=1e-12) and the reference's golden PySB trajectory.
+north_star tolerance: ODE trajectories within rtol 1e-6."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ode
+from oracle import priors as pr
+
+pytestmark = pytest.mark.gpu
+
+ODE_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_ode.npz"))
+
+
+def _simulate_on_device(network, sampled, Y, tspan, obs):
+    """Observable trajectory read back through the likelihood itself: with data = 0, kind 'sse'
+    and the mask on one time point, logL = -sim(t_i)^2."""
+    from gleipnir_b200.odegen import OdeNetworkLogLikelihood
+    out = np.zeros(len(tspan))
+    for i in range(len(tspan)):
+        like = OdeNetworkLogLikelihood(network, sampled, tspan, {obs: (np.zeros(1), None, [i])}, kind="sse")
+        out[i] = np.sqrt(-like(np.asarray(Y, dtype=float)))
+    return out
+
+
+def test_model_0_trajectory_matches_reference_golden(cuda, g):
+    """The one genuine ScipyOdeSimulator trajectory in the reference tree."""
+    from gleipnir_b200 import networks
+    net = networks.model_0()
+    ts = g["model_0/tspan"]
+    sim = _simulate_on_device(net, ["kf", "kr"], np.log10([1.5e-5, 1.2e-4]), ts, "AB_complex")
+    np.testing.assert_allclose(sim[-10:], g["model_0/AB_complex_last10"], rtol=ODE_RTOL)
+    _, obs = ode.simulate(net.description(), net.param_values, ts)
+    np.testing.assert_allclose(sim[1:], obs[1:, 2], rtol=1e-7)            # vs the tight-tolerance oracle
+
+
+@pytest.mark.parametrize("kind", ["snlpdf", "mse", "sse"])
+def test_dimerization_loglike_matches_oracle(cuda, g, kind):
+    """C4 inputs: Y = log10(kf, kr) drawn from the shipped priors norm(-3,1), norm(0,1)."""
+    from gleipnir_b200 import networks
+    from gleipnir_b200.odegen import OdeNetworkLogLikelihood
+    net = networks.dimerization()
+    data, sd, ts = g["dimerization/data"], g["dimerization/sd"], g["dimerization/tspan"]
+    like = OdeNetworkLogLikelihood(net, ["kf", "kr"], ts, {"A_dimer": (data, 10.0 * sd, None)}, kind=kind)
+    rng = np.random.default_rng(4)
+    Y = np.stack([rng.normal(-3.0, 1.0, 64), rng.normal(0.0, 1.0, 64)], axis=1)
+    got = like.evaluate(Y)
+    rows = [(1, data, 10.0 * sd, np.ones(51))]
+    want = np.array([ode.loglike(net.description(), [0, 1], y, ts, rows, kind) for y in Y])
+    np.testing.assert_allclose(got, want, rtol=ODE_RTOL)
+    # scalar host protocol + device-tensor protocol agree with the batch
+    assert like(Y[0]) == got[0]
+    assert np.array_equal(like.evaluate(cuda.as_tensor(Y, device="cuda")).cpu().numpy(), got)
+
+
+def test_stiff_parameter_corners_do_not_fail(cuda, g):
+    """10 decades of rate constants (run_jarm_multinest.py:63 spans 5e-8..1.9e3): every solve must
+    finish (finite logL) and agree with the oracle."""
+    from gleipnir_b200 import networks
+    from gleipnir_b200.odegen import OdeNetworkLogLikelihood
+    net = networks.dimerization()
+    data, sd, ts = g["dimerization/data"], g["dimerization/sd"], g["dimerization/tspan"]
+    like = OdeNetworkLogLikelihood(net, ["kf", "kr"], ts, {"A_dimer": (data, 10.0 * sd, None)})
+    Y = np.array([[a, b] for a in (-7.3, -3.0, 1.0, 3.28) for b in (-7.3, 0.0, 3.28)])
+    got = like.evaluate(Y)
+    rows = [(1, data, 10.0 * sd, np.ones(51))]
+    want = np.array([ode.loglike(net.description(), [0, 1], y, ts, rows) for y in Y])
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, want, rtol=ODE_RTOL)
+
+
+def test_nested_sampling_run_on_dimerization_matches_oracle_engine(cuda, g):
+    """Whole NS run with the ODE likelihood in the walkers vs the CPU oracle engine whose
+    likelihood is the SciPy stand-in: same Philox counters -> same dead slots; values to 1e-6."""
+    from gleipnir_b200 import networks
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.odegen import OdeNetworkLogLikelihood
+    from oracle.engine import Engine
+    from oracle.likelihoods import Model
+    net = networks.dimerization()
+    data, sd, ts = g["dimerization/data"], g["dimerization/sd"], g["dimerization/tspan"]
+    like = OdeNetworkLogLikelihood(net, ["kf", "kr"], ts, {"A_dimer": (data, 10.0 * sd, None)})
+    rows = [(1, data, 10.0 * sd, np.ones(51))]
+    desc = net.description()
+    table = [(pr.GL_PRIOR_NORM, -3.0, 1.0), (pr.GL_PRIOR_NORM, 0.0, 1.0)]      # run_NS_dimerization_model.py:69-71
+    N, k, n_deaths = 24, 3, 36
+    o = Engine(table, Model("callable", 2, fn=lambda y: ode.loglike(desc, [0, 1], y, ts, rows)), N, batch_k=k,
+               iterations=3, tuning_cycles=1, seed=11)
+    want = o.run(n_deaths)
+    eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, iterations=3, tuning_cycles=1, seed=11)
+    eng.init(); eng.advance(n_deaths); eng.finalize()
+    tab, idx, _ = eng.dead_table()
+    st = eng.state()
+    assert np.array_equal(idx[:n_deaths], want["dead_index"])
+    np.testing.assert_allclose(tab[:, 0], want["dead"][:, 0], rtol=ODE_RTOL)
+    np.testing.assert_allclose(tab[:, 2:], want["dead"][:, 2:], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(st.log_z, want["logZ"], rtol=ODE_RTOL)
+
+
+def test_reference_dimerization_script_flow(cuda, g):
+    """examples/pysb_dimerization_model/run_NS_dimerization_model.py with the drop-in classes."""
+    from scipy.stats import norm
+    from gleipnir.nestedsampling import NestedSampling
+    from gleipnir.nestedsampling.samplers import MetropolisComponentWiseHardNSRejection
+    from gleipnir.nestedsampling.stopping_criterion import NumberOfIterations
+    from gleipnir.sampled_parameter import SampledParameter
+    from gleipnir_b200 import networks
+    from gleipnir_b200.odegen import OdeNetworkLogLikelihood
+    data, sd, ts = g["dimerization/data"], g["dimerization/sd"], g["dimerization/tspan"]
+    loglikelihood = OdeNetworkLogLikelihood(networks.dimerization(), ["kf", "kr"], ts,
+                                            {"A_dimer": (data, 10.0 * sd, None)})
+    sps = [SampledParameter('kf', norm(loc=np.log10(0.001), scale=1.)),
+           SampledParameter('kr', norm(loc=np.log10(1.0), scale=1.))]
+    population_size = 100
+    NS = NestedSampling(sampled_parameters=sps, loglikelihood=loglikelihood,
+                        sampler=MetropolisComponentWiseHardNSRejection(iterations=20, tuning_cycles=1),
+                        population_size=population_size, stopping_criterion=NumberOfIterations(10 * population_size),
+                        seed=1)
+    logz, err = NS.run()
+    assert np.isfinite(logz) and err > 0
+    assert NS.dead_points.shape[1] == 4 and list(NS.dead_points.columns[2:]) == ['kf', 'kr']
+    # the data were generated near kf*c = 2.5e-4, kr = 1: the best fit must beat
+    # the prior-centre likelihood by a wide margin
+    assert NS.max_loglikelihood() > loglikelihood(np.array([-3.0, 0.0]))
+    assert len(NS.posteriors()) == 2
