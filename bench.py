@@ -97,7 +97,7 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------
 def _cpu_sample(args):
     """One bounded sample of the workload with the reference-as-shipped port; (evals, seconds)."""
-    seed, population, max_iter = args
+    seed, population, max_iter = args[:3]
     import warnings
     from scipy.stats import uniform
     from oracle import reference_port as rp
@@ -137,7 +137,7 @@ def run_reference_arm(args):
         return 0
     w = WORKLOAD
     cores = os.cpu_count() or 1
-    population, max_iter = w["population"], 40     # 10^4 rvs + 10^4 logL + 39 sampler calls per process
+    population, max_iter = w["population"], 120    # 10^4 rvs + 10^4 logL + 119 sampler calls per process
     per_step = []
     total_evals = 0
     for i in range(args.warmup + args.steps):
@@ -201,9 +201,12 @@ def run_b200_arm(args):
     from gleipnir_b200.likelihoods import EggCartonLogLikelihood
     lib = L.load()
     w = WORKLOAD
-    N, d = w["population"], w["d"]
+    d = w["d"]
+    N = w["population"] * world            # weak scaling: 10^4 live points per GPU, one global run
     k = args.batch_k if args.batch_k else N // 10
     n_deaths = death_count(N, w["cutoff"])
+    from gleipnir_b200.sharded import TorchDistComm, run_sharded, shard_bounds
+    comm = TorchDistComm() if world > 1 else None
     table = [(L.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
     like = EggCartonLogLikelihood(d)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")     # > 126 MB L2
@@ -215,23 +218,31 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
 
     def one_run(seed, profile=False):
-        eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, iterations=w["iterations"],
-                           burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=seed,
-                           walker_lanes=args.walker_lanes)
+        skw = dict(iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0,
+                   seed=seed, walker_lanes=args.walker_lanes)
+        if world > 1:                      # one shard per rank; L* by all-gather (NCCL)
+            off, n_loc = shard_bounds(N, world, rank)
+            eng = DeviceEngine(table, like.device_model(), n_loc, k, n_deaths, row_offset=off, global_population=N,
+                               **skw)
+        else:
+            eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, **skw)
         if profile:
             eng.profile_enable(True)
         flush.zero_()                      # evict L2 between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.init()
-        eng.advance(n_deaths)
-        eng.finalize()
+        if world > 1:
+            run_sharded([eng], comm, n_deaths, k)
+        else:
+            eng.init()
+            eng.advance(n_deaths)
+            eng.finalize()
         e1.record()
         e1.synchronize()
         return eng, e0.elapsed_time(e1)
 
     for i in range(args.warmup):
-        one_run(1000 * rank + i)
+        one_run(i)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -240,7 +251,7 @@ def run_b200_arm(args):
     walk_ms = walk_launches = sel_ms = sel_launches = 0
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        eng, ms = one_run(1000 * rank + 100 + i, profile=True)
+        eng, ms = one_run(100 + i, profile=True)
         st = eng.state()
         times.append(ms)
         evals += st.n_evals
@@ -278,7 +289,7 @@ def run_b200_arm(args):
     for i in range(args.steps):
         ns, t = one_e2e(500 + i)
         e2e_t += t
-        e2e_evals += ns._n_evals
+        e2e_evals += ns._n_evals / world           # sharded runs report the global count on every rank
     barrier()
 
     # max over ranks (device time), sum of evals over ranks
@@ -303,7 +314,7 @@ def run_b200_arm(args):
         pass
     dfma_peak = measure_dfma_peak(torch, lib, L)
     sweeps = 20 * w["tuning_cycles"] + w["iterations"] + w["burn_in"]
-    walk_evals_per_step = k * d * sweeps
+    walk_evals_per_step = (k / world) * d * sweeps          # walkers of this rank (k/world on average)
     n_walk_steps = walk_launches / (w["tuning_cycles"] + 1)
     avg_launch_s = (walk_ms * 1e-3) / max(walk_launches, 1)
     flop_per_eval = FLOP_PER_TRIAL_EGGCARTON_D2
@@ -318,26 +329,36 @@ def run_b200_arm(args):
                     select_hbm=dict(bound="hbm", achieved=(8.0 * N) / (1e-3 * sel_ms / max(sel_launches, 1)) / 1e9,
                                     peak=peaks.get("hbm_gbs"), unit="GB/s"))
     # ---- CPU baseline: bounded sample on one host core ---------------------------------------
-    cpu_evals, cpu_wall = cpu_sample_parallel(1, N, 40)
-    cpu_value = cpu_evals / cpu_wall
-    evals_full = N + (n_deaths - 1) * (1 + sweeps * d)
+    # init (N rvs + N logL) and the per-iteration sampler cost are timed separately so that the
+    # extrapolation to the full run is t_init + (n_deaths - 1) * t_iteration
+    cpu = None
+    if world == 1:
+        ev1, t1 = cpu_sample_parallel(1, N, 1)
+        cpu_evals, cpu_wall = cpu_sample_parallel(1, N, 120)
+        t_iter = (cpu_wall - t1) / 119.0
+        evals_full = N + (n_deaths - 1) * (1 + sweeps * d)
+        cpu_full_s = t1 + (n_deaths - 1) * t_iter
+        cpu_value = evals_full / cpu_full_s
+        cpu = dict(value=cpu_value, unit="evals/s", cores=1, kind="port",
+                   sample="reference-as-shipped port (oracle/reference_port.py), N=%d init (%.2f s) + "
+                          "120 iterations (%d evals, %.1f s); value = full-run evals / (t_init + "
+                          "(n_deaths-1)*t_iteration)" % (N, t1, cpu_evals, cpu_wall),
+                   time_to_converged_logZ_s_extrapolated=cpu_full_s)
     line = dict(metric="logL evals/sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=w["name"], population_per_gpu=N, batch_k=k, n_deaths=n_deaths,
+                config=dict(workload=w["name"], population_per_gpu=w["population"], population_global=N, batch_k=k, n_deaths=n_deaths,
                             walker_lanes=args.walker_lanes or "auto",
                             sampler="MetropolisComponentWiseHardNSRejection(iterations=50, tuning_cycles=2)",
                             l2="flushed between timed runs (256 MB memset)",
-                            parallelism="replicas" if world > 1 else "single"),
+                            parallelism=("live set sharded over %d ranks, all-gather of k logL per step" % world)
+                            if world > 1 else "single"),
                 clocks=clk, gpu_launches=int(float(tot[2])),
                 e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int(24 * d + ctypes.sizeof(L.gl_ns_config)),
                          d2h_bytes_per_step=int(last_rows * (8 * (d + 2) + 8 + 4) + ctypes.sizeof(L.gl_ns_state)),
                          ms_per_step=1e3 * t_e2e / args.steps),
                 roofline=roofline,
-                cpu_baseline=dict(value=cpu_value, unit="evals/s", cores=1, kind="port",
-                                  sample="reference-as-shipped port, N=%d init + 40 iterations (%d evals, %.1f s)"
-                                         % (N, cpu_evals, cpu_wall),
-                                  time_to_converged_logZ_s_extrapolated=evals_full / cpu_value),
+                cpu_baseline=cpu,
                 time_to_converged_logZ_s=t_dev / args.steps,
                 logZ_mean=float(np.mean(logzs)), logZ_std=float(np.std(logzs)), logZ_err_reported=float(np.mean(errs)),
                 logZ_truth=w["truth_logz"])

@@ -85,6 +85,10 @@ _SIGNATURES = {
     "gl_ns_inject": (c_int, [_P, _P, _P, c_int32, _P]),
     "gl_ns_finalize": (c_int, [_P, _P]),
     "gl_ns_read_state": (c_int, [_P, POINTER(gl_ns_state), _P]),
+    "gl_ns_shard_candidates": (c_int, [_P, c_int32, _P, _P]),
+    "gl_ns_shard_commit": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
+    "gl_ns_shard_final_partial": (c_int, [_P, _P, _P]),
+    "gl_ns_shard_finalize": (c_int, [_P, _P, c_int32, c_int32, _P]),
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),

@@ -51,12 +51,16 @@ __global__ void __launch_bounds__(256) record_kernel(EngineState *S, const long 
 }
 
 // ---- accumulate: evidence / information update for the batch (:118-125,160-167) ----------
+// k_override < 0: the batch is the engine's own (k = S->k_cur, all rows local).  Sharded run:
+// k_override = global batch size, dead_list/logl index the all-gathered candidate array and the
+// local row count S->k_cur was set by shard_local_kernel.
 __global__ void __launch_bounds__(1024) accumulate_kernel(EngineState *S, const long long *__restrict__ dead_list,
                                                           const double *__restrict__ logl, double n_global,
-                                                          long long n_target, long long capacity) {
+                                                          long long n_target, long long capacity, int k_override) {
     __shared__ double scratch[33];
     __shared__ unsigned long long kscratch[33];
-    const int k = S->k_cur;
+    const int k = k_override >= 0 ? k_override : S->k_cur;
+    const int k_rows = S->k_cur;
     if (k <= 0) return;
     const double logw = S->logX - log(n_global + 1.0);
     const double w = exp(logw);
@@ -115,9 +119,46 @@ __global__ void __launch_bounds__(1024) accumulate_kernel(EngineState *S, const 
         S->H_lin += hl;
         S->logX += log((n_global - (double)k + 1.0) / (n_global + 1.0));
         S->n_dead += k;
-        if (S->n_rows + k <= capacity) S->n_rows += k;
+        if (S->n_rows + k_rows <= capacity) S->n_rows += k_rows;
         S->lstar = key_to_double(mk);
         S->do_walk = S->n_dead < n_target;
+    }
+}
+
+// ---- sharded run helpers -------------------------------------------------------------------
+// candidates: logL of this rank's k worst slots, in ascending slot order
+__global__ void __launch_bounds__(256) shard_gather_kernel(const long long *__restrict__ cand_list,
+                                                           const double *__restrict__ logl, int k,
+                                                           double *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) out[i] = logl[cand_list[i]];
+}
+
+// `positions` = the global k worst as ascending positions in the gathered [G*k] array (rank-major,
+// slot-ascending inside a rank, i.e. global-index order).  This rank's share is the contiguous run
+// of positions inside [rank*k, (rank+1)*k): translate it back to local slots, flag them dead and
+// publish the local batch size.
+__global__ void __launch_bounds__(256) shard_local_kernel(EngineState *S, const long long *__restrict__ positions,
+                                                          const long long *__restrict__ cand_list, int k, int rank,
+                                                          long long *__restrict__ dead_list,
+                                                          unsigned char *__restrict__ is_dead) {
+    __shared__ int s_start, s_end;
+    if (threadIdx.x == 0) {
+        const long long lo_pos = (long long)rank * k, hi_pos = lo_pos + k;
+        int a = 0, b = k;                          // lower_bound(positions, lo_pos)
+        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < lo_pos) a = m + 1; else b = m; }
+        s_start = a;
+        b = k;
+        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < hi_pos) a = m + 1; else b = m; }
+        s_end = a;
+        S->k_cur = s_end - s_start;
+        S->do_walk = 0;
+    }
+    __syncthreads();
+    const int start = s_start, n_loc = s_end - s_start;
+    for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
+        const long long slot = cand_list[positions[start + i] - (long long)rank * k];
+        dead_list[i] = slot;
+        is_dead[slot] = 1;
     }
 }
 
@@ -354,7 +395,8 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
 
 // ---- end of refill: clear the dead flags, persist widths, advance the step ----------------
 __global__ void __launch_bounds__(256) end_walk_kernel(EngineState *S, const long long *__restrict__ dead_list,
-                                                       unsigned char *is_dead, int d, int tuning_cycles) {
+                                                       unsigned char *is_dead, int d, int tuning_cycles,
+                                                       long long evals_per_walker) {
     const int k = S->k_cur;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x)
         is_dead[dead_list[i]] = 0;
@@ -369,6 +411,7 @@ __global__ void __launch_bounds__(256) end_walk_kernel(EngineState *S, const lon
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S->n_evals += (unsigned long long)((long long)k * evals_per_walker);
         S->step += 1;
         S->do_walk = 0;
         S->k_cur = 0;
@@ -476,14 +519,18 @@ __global__ void __launch_bounds__(FIN_THREADS) final_partial_kernel(const double
     }
 }
 
-__global__ void final_combine_kernel(EngineState *S, const double *partials, int nblocks) {
+// partials [local_first, local_first + local_count) belong to this engine (all of them when unsharded)
+__global__ void final_combine_kernel(EngineState *S, const double *partials, int nblocks, int local_first,
+                                     int local_count) {
     LsePair p{-INFINITY, 0.0};
-    double lin = 0.0, cnt = 0.0;
+    double lin = 0.0, cnt = 0.0, cnt_local = 0.0;
     for (int b = 0; b < nblocks; ++b) {
         p = lse_combine(p, LsePair{partials[4 * b], partials[4 * b + 1]});
         lin += partials[4 * b + 2];
         cnt += partials[4 * b + 3];
+        if (b >= local_first && b < local_first + local_count) cnt_local += partials[4 * b + 3];
     }
+    S->fin_n_local = (long long)cnt_local;
     if (cnt <= 0.0) return;
     const double X = exp(S->logX);
     const double lm = lin / cnt;                                  // mean likelihood (:187)
@@ -516,7 +563,7 @@ __global__ void __launch_bounds__(256) final_rows_kernel(EngineState *S, const l
     const int k = S->k_cur;                      // unreplaced slots of the last batch
     const long long base = S->n_rows;
     const long long n_surv = S->fin_n;
-    if (n_surv <= 0 || base + n_surv > capacity) return;
+    if (n_surv <= 0 || base + S->fin_n_local > capacity) return;
     const double aw = exp(S->logX) / (double)n_surv;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
          i += (long long)gridDim.x * blockDim.x) {
@@ -537,7 +584,7 @@ __global__ void __launch_bounds__(256) final_rows_kernel(EngineState *S, const l
 }
 
 __global__ void final_done_kernel(EngineState *S, long long capacity) {
-    if (S->fin_n > 0 && S->n_rows + S->fin_n <= capacity) S->n_rows += S->fin_n;
+    if (S->fin_n > 0 && S->n_rows + S->fin_n_local <= capacity) S->n_rows += S->fin_n_local;
     S->finalized = 1;
 }
 
@@ -560,6 +607,8 @@ struct gl_ns {
     long long *dead_list;
     unsigned char *is_dead;
     double *scratch_x, *scratch_l, *tmp_k, *fin_partials;
+    long long *cand_list, *positions;             // sharded run scratch ([k] each)
+    gl::SelectState *sel2;                        // selection state for the gathered candidates
     // host mirrors (deterministic arithmetic; no device reads needed to drive the loop)
     long long h_n_dead, h_n_evals, h_launches;
     int h_step, h_k_last;
@@ -576,7 +625,8 @@ namespace gl {
 static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct WorkspaceLayout {
-    size_t off_state, off_sel, off_pt, off_list, off_isdead, off_sx, off_sl, off_tmp, off_fin, total;
+    size_t off_state, off_sel, off_pt, off_list, off_isdead, off_sx, off_sl, off_tmp, off_fin, off_cand, off_pos,
+        off_sel2, total;
 };
 
 static WorkspaceLayout workspace_layout(const gl_ns_config &c, int d) {
@@ -592,6 +642,9 @@ static WorkspaceLayout workspace_layout(const gl_ns_config &c, int d) {
     L.off_sl = o;     o += align256(sizeof(double) * k);
     L.off_tmp = o;    o += align256(sizeof(double) * k);
     L.off_fin = o;    o += align256(sizeof(double) * 4 * FIN_MAX_BLOCKS);
+    L.off_cand = o;   o += align256(sizeof(long long) * k);
+    L.off_pos = o;    o += align256(sizeof(long long) * k);
+    L.off_sel2 = o;   o += align256(sizeof(SelectState));
     L.total = o;
     return L;
 }
@@ -607,8 +660,8 @@ static int check_config(const gl_ns_config *cfg, int d) {
     GL_REQUIRE(cfg->proposal == GL_PROPOSAL_UNIFORM || cfg->proposal == GL_PROPOSAL_NORMAL, "unknown proposal");
     GL_REQUIRE(cfg->dead_capacity >= 1, "dead_capacity must be >= 1");
     GL_REQUIRE(cfg->walker_lanes >= 0 && cfg->walker_lanes <= 32, "walker_lanes outside [0, 32]");
-    GL_REQUIRE(cfg->row_offset == 0 && cfg->global_population == cfg->population_size,
-               "sharded engines are driven through the multi-GPU host loop (not yet in this build)");
+    GL_REQUIRE(cfg->row_offset >= 0 && cfg->global_population >= cfg->population_size + cfg->row_offset,
+               "shard [row_offset, row_offset + population_size) must lie inside the global population");
     return GL_OK;
 }
 
@@ -683,7 +736,7 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
             ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
             ns->buf.dead_step);
         accumulate_kernel<<<1, 1024, 0, st>>>(ns->S, ns->dead_list, ns->buf.logl, n_global, n_target,
-                                              ns->cfg.dead_capacity);
+                                              ns->cfg.dead_capacity, -1);
         GL_CHECK_LAUNCH();
     }
     long long k = n_target - ns->h_n_dead;
@@ -696,9 +749,9 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
     return GL_OK;
 }
 
-static int end_walk_launch(gl_ns *ns, cudaStream_t st) {
+static int end_walk_launch(gl_ns *ns, cudaStream_t st, long long evals_per_walker) {
     end_walk_kernel<<<blocks_for(ns->cfg.batch_k, 256, 4), 256, 0, st>>>(ns->S, ns->dead_list, ns->is_dead, ns->d,
-                                                                          ns->cfg.tuning_cycles);
+                                                                          ns->cfg.tuning_cycles, evals_per_walker);
     GL_CHECK_LAUNCH();
     ns->h_launches += 1;
     ns->h_step += 1;
@@ -713,9 +766,7 @@ static int refill_launch(gl_ns *ns, cudaStream_t st) {
     prof_mark(ns, ns->ev_walk, st);
     ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
     ns->h_launches += ns->cfg.tuning_cycles + 1;
-    ns->h_n_evals += (long long)ns->h_k_last *
-                     (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
-    return end_walk_launch(ns, st);
+    return end_walk_launch(ns, st, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d);
 }
 
 }  // namespace gl
@@ -762,6 +813,9 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->scratch_l = (double *)(w + L.off_sl);
     ns->tmp_k = (double *)(w + L.off_tmp);
     ns->fin_partials = (double *)(w + L.off_fin);
+    ns->cand_list = (long long *)(w + L.off_cand);
+    ns->positions = (long long *)(w + L.off_pos);
+    ns->sel2 = (gl::SelectState *)(w + L.off_sel2);
     ns->h_n_dead = ns->h_n_evals = ns->h_launches = 0;
     ns->h_step = ns->h_k_last = 0;
     ns->initialized = ns->pending_refill = ns->finalized = false;
@@ -790,6 +844,7 @@ int gl_ns_init(gl_ns *ns, int32_t skip_population, void *stream) {
     memset(&h, 0, sizeof(h));
     h.M = -INFINITY;
     h.lstar = -INFINITY;
+    h.n_evals = skip_population ? 0ull : (unsigned long long)ns->cfg.population_size;
     GL_CUDA(cudaMemcpyAsync(ns->S, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     gl::PriorTable pt;
     memset(&pt, 0, sizeof(pt));
@@ -856,7 +911,7 @@ int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_dev, in
                                               ns->buf.live, ns->buf.logl);
     GL_CHECK_LAUNCH();
     ns->h_launches += 2;
-    return gl::end_walk_launch(ns, st);
+    return gl::end_walk_launch(ns, st, 0);
 }
 
 int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream) {
@@ -897,7 +952,7 @@ int gl_ns_finalize(gl_ns *ns, void *stream) {
     blocks = (N + chunk - 1) / chunk;
     gl::final_partial_kernel<<<(int)blocks, gl::FIN_THREADS, 0, st>>>(ns->buf.logl, ns->is_dead, N, chunk,
                                                                       ns->fin_partials);
-    gl::final_combine_kernel<<<1, 1, 0, st>>>(ns->S, ns->fin_partials, (int)blocks);
+    gl::final_combine_kernel<<<1, 1, 0, st>>>(ns->S, ns->fin_partials, (int)blocks, 0, (int)blocks);
     gl::final_rows_kernel<<<gl::blocks_for(N, 256, 8), 256, 0, st>>>(
         ns->S, ns->dead_list, ns->is_dead, ns->buf.live, ns->buf.logl, N, ns->d, ns->cfg.row_offset,
         ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
@@ -918,7 +973,7 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
     memset(out, 0, sizeof(*out));
     out->n_dead = h.n_dead;
     out->n_rows = h.n_rows;
-    out->n_evals = ns->h_n_evals;
+    out->n_evals = (int64_t)h.n_evals;
     out->n_launches = ns->h_launches;
     out->step = h.step;
     out->finalized = h.finalized;
@@ -943,6 +998,82 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
 }  // extern "C"
 
 extern "C" {
+
+// ---- sharded run (one engine per rank; the caller all-gathers between the two calls) ------------
+int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *stream) {
+    GL_REQUIRE(ns != nullptr && cand_logl_dev != nullptr, "NULL argument");
+    if (!ns->initialized || ns->finalized || ns->pending_refill) {
+        gl::set_error("gl_ns_shard_candidates: engine not ready (init first / refill the previous batch)");
+        return GL_ESTATE;
+    }
+    GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k && k < ns->cfg.population_size, "k=%d outside [1, min(batch_k, N_local-1)]", k);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = gl::select_launch(ns->buf.logl, ns->cfg.population_size, nullptr, k, 0, ns->cand_list, nullptr, nullptr,
+                               ns->sel, st);
+    if (rc) return rc;
+    gl::shard_gather_kernel<<<gl::blocks_for(k, 256, 4), 256, 0, st>>>(ns->cand_list, ns->buf.logl, k, cand_logl_dev);
+    GL_CHECK_LAUNCH();
+    ns->h_launches += gl::SEL_PASSES + 2 + 1;
+    return GL_OK;
+}
+
+int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                       void *stream) {
+    GL_REQUIRE(ns != nullptr && gathered_logl_dev != nullptr, "NULL argument");
+    GL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad world/rank");
+    GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k, "k=%d outside [1, batch_k]", k);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double n_global = (double)ns->cfg.global_population;
+    int rc = gl::select_launch(gathered_logl_dev, (long long)world * k, nullptr, k, 0, ns->positions, nullptr, nullptr,
+                               ns->sel2, st);
+    if (rc) return rc;
+    gl::shard_local_kernel<<<1, 256, 0, st>>>(ns->S, ns->positions, ns->cand_list, k, rank, ns->dead_list,
+                                              ns->is_dead);
+    gl::record_kernel<<<gl::blocks_for((long long)k * ns->d, 256, 8), 256, 0, st>>>(
+        ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
+        ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
+        ns->buf.dead_step);
+    gl::accumulate_kernel<<<1, 1024, 0, st>>>(ns->S, ns->positions, gathered_logl_dev, n_global, INT64_MAX,
+                                              ns->cfg.dead_capacity, k);
+    GL_CHECK_LAUNCH();
+    ns->h_launches += gl::SEL_PASSES + 2 + 3;
+    ns->h_n_dead += k;
+    ns->h_k_last = -1;                     // local batch size is only known on the device
+    ns->pending_refill = true;
+    return GL_OK;
+}
+
+// partial[4] = (m, s, linear sum, count) of this rank's survivors (nested_sampling.py:184-187)
+int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *stream) {
+    GL_REQUIRE(ns != nullptr && partial_dev != nullptr, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = ns->cfg.population_size;
+    gl::final_partial_kernel<<<1, gl::FIN_THREADS, 0, st>>>(ns->buf.logl, ns->is_dead, N, N, partial_dev);
+    GL_CHECK_LAUNCH();
+    ns->h_launches += 1;
+    return GL_OK;
+}
+
+int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank, void *stream) {
+    GL_REQUIRE(ns != nullptr && gathered_partials_dev != nullptr && world >= 1 && rank >= 0 && rank < world,
+               "bad argument");
+    if (!ns->initialized || ns->finalized) {
+        gl::set_error("gl_ns_shard_finalize: engine not initialised or already finalized");
+        return GL_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = ns->cfg.population_size;
+    gl::final_combine_kernel<<<1, 1, 0, st>>>(ns->S, gathered_partials_dev, world, rank, 1);
+    gl::final_rows_kernel<<<gl::blocks_for(N, 256, 8), 256, 0, st>>>(
+        ns->S, ns->dead_list, ns->is_dead, ns->buf.live, ns->buf.logl, N, ns->d, ns->cfg.row_offset,
+        ns->cfg.dead_capacity, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx,
+        ns->buf.dead_step);
+    gl::final_done_kernel<<<1, 1, 0, st>>>(ns->S, ns->cfg.dead_capacity);
+    GL_CHECK_LAUNCH();
+    ns->h_launches += 3;
+    ns->finalized = true;
+    return GL_OK;
+}
 
 int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");

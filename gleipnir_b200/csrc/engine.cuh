@@ -23,7 +23,9 @@ struct EngineState {                 // one instance in device memory per engine
     unsigned int acc[GL_MAX_TUNING_CYCLES][GL_MAX_DIM];   // pooled acceptance counts of this step
     // finalize scratch
     double fin_m, fin_s, fin_lin;
-    long long fin_n;
+    long long fin_n;                 // survivors over ALL ranks (weight denominator)
+    long long fin_n_local;           // survivors of this engine (rows it appends)
+    unsigned long long n_evals;      // log-likelihood evaluations performed by this engine
 };
 
 struct WalkParams {                  // by-value kernel parameter

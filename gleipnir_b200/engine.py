@@ -20,7 +20,8 @@ class DeviceEngine(object):
     """One device-resident NS run: live set, dead-point log, accumulators, widths."""
 
     def __init__(self, prior_table, model_handle, population_size, batch_k, n_deaths_capacity, iterations=100,
-                 burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None, walker_lanes=0):
+                 burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None, walker_lanes=0, row_offset=0,
+                 global_population=None):
         torch = _torch()
         self.lib = _lib.load()
         self.d = len(prior_table)
@@ -30,7 +31,8 @@ class DeviceEngine(object):
         self.cfg = _lib.gl_ns_config(population_size=self.N, batch_k=int(batch_k), iterations=int(iterations),
                                      burn_in=int(burn_in), tuning_cycles=int(tuning_cycles),
                                      proposal=int(proposal), walker_lanes=int(walker_lanes), seed=int(seed) & (2 ** 64 - 1),
-                                     dead_capacity=cap, row_offset=0, global_population=self.N)
+                                     dead_capacity=cap, row_offset=int(row_offset),
+                                     global_population=int(global_population or self.N))
         ws = self.lib.gl_ns_workspace_bytes(ctypes.byref(self.cfg), self.d)
         if ws < 0:
             _lib.check(int(ws))
@@ -93,6 +95,28 @@ class DeviceEngine(object):
 
     def force_multipass_select(self, enable=True):
         _lib.check(self.lib.gl_ns_force_multipass_select(self._h, 1 if enable else 0))
+
+    # ---- sharded run (one engine per rank; see gleipnir_b200/sharded.py) ---------------------
+    def candidates(self, k):
+        torch = _torch()
+        out = torch.empty(int(k), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gl_ns_shard_candidates(self._h, int(k), out.data_ptr(), self._stream()))
+        return out
+
+    def commit(self, gathered, world, rank, k):
+        self._gathered = gathered                       # must outlive the enqueued kernels
+        _lib.check(self.lib.gl_ns_shard_commit(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
+                                               self._stream()))
+
+    def final_partial(self):
+        torch = _torch()
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gl_ns_shard_final_partial(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def finalize_sharded(self, gathered, world, rank):
+        self._gathered = gathered
+        _lib.check(self.lib.gl_ns_shard_finalize(self._h, gathered.data_ptr(), int(world), int(rank), self._stream()))
 
     def profile_enable(self, enable=True):
         _lib.check(self.lib.gl_ns_profile_enable(self._h, 1 if enable else 0))

@@ -12,6 +12,10 @@ optional, defaults keep the reference call verbatim):
     seed      Philox key.  Default: drawn from numpy's global RNG, so ``np.random.seed``
               still makes a script reproducible.
     device    torch device (default: current CUDA device).
+    sharded   None (default): shard the live set over the ranks of an initialised
+              ``torch.distributed`` process group when there is more than one (one process per
+              GPU; ``population_size`` is then the GLOBAL population, divisible by the world
+              size); False: run the whole population on this process's GPU.
 
 The whole run -- prior draws, log-likelihoods, k-worst selection, evidence / information
 accumulation, constrained Metropolis walkers, stop test -- is device resident (see
@@ -38,7 +42,7 @@ def _default_sampler():
 class NestedSampling(NestedSamplingBase):
 
     def __init__(self, sampled_parameters, loglikelihood, population_size, sampler=None,
-                 stopping_criterion=None, batch_k=None, seed=None, device=None):
+                 stopping_criterion=None, batch_k=None, seed=None, device=None, sharded=None):
         self.sampled_parameters = sampled_parameters
         self._sampled_parameters_dict = {sp.name: sp for sp in sampled_parameters}
         self.loglikelihood = loglikelihood
@@ -50,6 +54,7 @@ class NestedSampling(NestedSamplingBase):
         self.batch_k = batch_k
         self.seed = seed
         self.device = device
+        self.sharded = sharded
 
         self._alpha = population_size / (population_size + 1)
         self._evidence = 0.0
@@ -84,6 +89,49 @@ class NestedSampling(NestedSamplingBase):
             return int(crit.death_count(self))
         return None
 
+    def _dist_world(self):
+        if self.sharded is False:
+            return None
+        try:
+            import torch.distributed as dist
+        except ImportError:          # pragma: no cover
+            return None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+        if self.sharded:
+            raise RuntimeError("sharded=True needs an initialised torch.distributed group with world_size > 1")
+        return None
+
+    def _run_sharded(self, dist, loglike, table, n, k, seed, scfg, n_deaths, verbose):
+        """One shard per rank, global threshold by all-gather (gleipnir_b200/sharded.py)."""
+        import torch
+        from ..sharded import TorchDistComm, run_sharded, shard_bounds
+        comm = TorchDistComm()
+        rank = comm.ranks[0]
+        seed_t = torch.tensor([seed], dtype=torch.int64, device="cuda")
+        dist.broadcast(seed_t, 0)                       # every rank must use rank 0's Philox key
+        off, n_loc = shard_bounds(n, comm.world, rank)
+        if k >= n_loc:
+            raise ValueError("batch_k (%d) must be smaller than the per-rank population (%d)" % (k, n_loc))
+        eng = DeviceEngine(table, loglike.device_model(), n_loc, k, n_deaths, seed=int(seed_t.item()),
+                           device=self.device, row_offset=off, global_population=n, **scfg)
+        self._engine = eng
+        run_sharded([eng], comm, n_deaths, k)
+        st = eng.state()
+        rows, idx, step = eng.dead_table()
+        parts = [None] * comm.world
+        dist.all_gather_object(parts, (rows, idx, step))
+        rows = np.concatenate([p[0] for p in parts])
+        idx = np.concatenate([p[1] for p in parts])
+        step = np.concatenate([p[2] for p in parts])
+        from ..engine import death_order
+        order = death_order(rows[:, 0], idx, step)
+        evals = torch.tensor([st.n_evals], dtype=torch.int64, device="cuda")
+        dist.all_reduce(evals)
+        live = [None] * comm.world
+        dist.all_gather_object(live, eng.live.cpu().numpy())
+        return st, rows[order], int(evals.item()), np.concatenate(live)
+
     def run(self, verbose=False):
         loglike = require_device_loglikelihood(self.loglikelihood)
         if loglike.ndim != len(self.sampled_parameters):
@@ -103,6 +151,13 @@ class NestedSampling(NestedSamplingBase):
             capacity = int(getattr(self.stopping_criterion, "max_iterations", 100 * n))
         else:
             capacity = n_deaths
+        dist = self._dist_world()
+        if dist is not None:
+            if chunked:
+                raise NotImplementedError("user-defined stopping criteria are not supported in sharded runs")
+            st, table_rows, n_evals, live = self._run_sharded(dist, loglike, table, n, k, seed, scfg, n_deaths,
+                                                              verbose)
+            return self._publish(st, table_rows, n_evals, live, n)
         if verbose:
             print("Generating the initial set of live points with population size {}...".format(n))
         eng = DeviceEngine(table, loglike.device_model(), n, k, capacity, seed=seed, device=self.device, **scfg)
@@ -135,9 +190,13 @@ class NestedSampling(NestedSamplingBase):
                     break
         eng.finalize()
         st = eng.state()
+        table_rows, _idx, _step = eng.dead_table()
+        return self._publish(st, table_rows, int(st.n_evals), eng.live.cpu().numpy(), n)
+
+    def _publish(self, st, table_rows, n_evals, live, n):
         self._state = st
         self._n_iterations = int(st.n_dead)
-        self._n_evals = int(st.n_evals)
+        self._n_evals = int(n_evals)
         self._log_evidence = float(st.log_z)
         with np.errstate(over="ignore"):
             self._evidence = float(np.exp(st.log_z))
@@ -145,10 +204,9 @@ class NestedSampling(NestedSamplingBase):
         self._H = float(st.h_linear)
         self._logZ_err = float(np.sqrt(max(self._information, 0.0) / n))
         self._evidence_error = float(np.exp(self._logZ_err))
-        table_rows, _idx, _step = eng.dead_table()
         names = [sp.name for sp in self.sampled_parameters]
         self._dead_points = pd.DataFrame(table_rows, columns=['log_l', 'weight'] + names)
-        self._live_points = pd.DataFrame(eng.live.cpu().numpy(), columns=names)
+        self._live_points = pd.DataFrame(live, columns=names)
         return self._log_evidence, self._logZ_err
 
     def _stopping_criterion(self):

@@ -211,6 +211,27 @@ GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 /* Copy the device state to the host (synchronises `stream`). */
 GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
 
+/* ---- sharded run: one engine per GPU/rank ------------------------------
+ * Rank r owns the contiguous global slots [row_offset, row_offset + population_size) of a
+ * population of `global_population`.  Per step, with k = global batch size:
+ *   1. gl_ns_shard_candidates   logL of this rank's k worst slots (ascending slot order);
+ *   2. the caller all-gathers the k doubles of every rank, rank-major (NCCL / torch.distributed)
+ *      -- the only data-path collective: the global likelihood threshold L*;
+ *   3. gl_ns_shard_commit       every rank selects the global k worst from the gathered
+ *      [world*k] array (position order == global-index order, so ties break as np.argmin
+ *      would), records ITS dead rows, and updates evidence/information/prior mass identically
+ *      and redundantly on every rank;
+ *   4. gl_ns_refill             walkers refill this rank's dead slots, seeded from this rank's
+ *      survivors.
+ * At the end gl_ns_shard_final_partial / all-gather of 4 doubles per rank /
+ * gl_ns_shard_finalize give the final live-point term (nested_sampling.py:183-203). */
+GL_API int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *stream);
+GL_API int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                              void *stream);
+GL_API int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *stream);
+GL_API int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank,
+                                void *stream);
+
 /* Populations whose ordering keys fit in shared memory (N <= 24576) use a single-CTA fused
  * kill kernel; this switch forces the general multi-launch selection path (used by tests so
  * that both paths are checked against each other and the oracle). */

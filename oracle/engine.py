@@ -117,8 +117,10 @@ class Accumulators(object):
 
 class Engine(object):
     def __init__(self, prior_table, model, population_size, batch_k=1, iterations=100, burn_in=0,
-                 tuning_cycles=0, proposal="uniform", seed=0):
+                 tuning_cycles=0, proposal="uniform", seed=0, row_offset=0, global_population=None):
         self.pt = [tuple(p) for p in prior_table]
+        self.row_offset = int(row_offset)
+        self.n_global = int(global_population or population_size)
         self.model = model
         self.N, self.d = int(population_size), len(prior_table)
         self.k = int(batch_k)
@@ -155,7 +157,7 @@ class Engine(object):
         return w
 
     def init(self, live=None, logl=None):
-        self.live = self.draw_rows(0, self.N) if live is None else np.array(live, dtype=np.float64)
+        self.live = self.draw_rows(self.row_offset, self.N) if live is None else np.array(live, dtype=np.float64)
         if logl is None:
             self.logl = self.model(self.live)
             self.n_evals += self.N
@@ -166,14 +168,14 @@ class Engine(object):
     # -- a8/a13/a14/a15: select + record one batch ---------------------------------------
     def kill(self, k):
         idx = select_k_worst(self.logl, k)
-        logw = self.logX - np.log(self.N + 1.0)
+        logw = self.logX - np.log(self.n_global + 1.0)
         w = np.exp(logw)
         for i in idx:
             self.dead_rows.append(np.concatenate(([self.logl[i], w], self.live[i])))
             self.dead_index.append(int(i))
             self.dead_batch.append(self.step)
         self.acc.add_terms(logw, self.logl[idx])
-        self.logX += np.log((self.N - k + 1.0) / (self.N + 1.0))
+        self.logX += np.log((self.n_global - k + 1.0) / (self.n_global + 1.0))
         self.n_dead += k
         self.last_dead = idx
         self.lstar = self.logl[idx[-1]]
@@ -192,7 +194,7 @@ class Engine(object):
         with np.errstate(all="ignore"):
             for t in range(t0, t0 + n_sweeps):
                 for j, (kind, p0, p1) in enumerate(self.pt):
-                    r, u = px.uniforms(self.seed, slots, self.step, t * d + j, px.GL_TAG_MOVE)
+                    r, u = px.uniforms(self.seed, slots + self.row_offset, self.step, t * d + j, px.GL_TAG_MOVE)
                     xj = cur[:, j]
                     nj = self._propose(r, xj, widths[j])
                     okp = pr.accept_prior(kind, p0, p1, xj, nj, u)
@@ -214,7 +216,7 @@ class Engine(object):
         for q, g in enumerate(slots):
             a = 0
             while True:
-                u, _ = px.uniforms(self.seed, int(g), self.step, a, px.GL_TAG_PICK)
+                u, _ = px.uniforms(self.seed, int(g) + self.row_offset, self.step, a, px.GL_TAG_PICK)
                 i = int(float(u) * self.N)
                 if not dead[i]:
                     break
@@ -238,7 +240,8 @@ class Engine(object):
         cur, cur_l = start.copy(), start_l.copy()
         for c in range(self.tc):
             acc = self._sweeps(slots, cur, cur_l, widths, c * 20, 20, True)
-            rate = acc / (20.0 * len(slots))
+            with np.errstate(all="ignore"):
+                rate = acc / (20.0 * len(slots))
             widths = np.where(rate < 0.2, widths * 0.66, np.where(rate > 0.6, widths * 1.33, widths))
         self.widths = widths
         cur, cur_l = start.copy(), start_l.copy()

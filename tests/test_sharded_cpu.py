@@ -1,0 +1,117 @@
+"""Host logic of the sharded run on CPUs: the product's SPMD loop
+(gleipnir_b200/sharded.py) driven with numpy oracle shards -- in one process (LocalComm) and
+over torch.distributed/gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from gleipnir_b200.sharded import LocalComm, TorchDistComm, run_sharded, shard_bounds
+from oracle import priors as pr
+from oracle.engine import Engine, select_k_worst
+from oracle.likelihoods import Model
+from oracle.sharded import OracleShard
+
+TABLE = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * 2
+KW = dict(iterations=4, tuning_cycles=1, seed=9)
+
+
+def _shards(world, n_global, k):
+    out = []
+    for r in range(world):
+        off, n_loc = shard_bounds(n_global, world, r)
+        out.append(OracleShard(TABLE, Model("iid_gaussian", 2), n_loc, batch_k=k, row_offset=off,
+                               global_population=n_global, **KW))
+    return out
+
+
+def test_shard_bounds():
+    assert shard_bounds(1000, 4, 2) == (500, 250)
+    with pytest.raises(ValueError):
+        shard_bounds(1001, 4, 0)
+
+
+def test_world_of_one_equals_unsharded_run():
+    n, k, deaths = 60, 6, 150
+    (sh,) = _shards(1, n, k)
+    run_sharded([sh], LocalComm(1), deaths, k)
+    want = Engine(TABLE, Model("iid_gaussian", 2), n, batch_k=k, **KW).run(deaths)
+    # a shard records a batch in slot order, the plain engine in death order: same rows per batch
+    nd = deaths
+    a = np.lexsort((sh.result["dead_index"], sh.result["dead_batch"]))
+    b = np.lexsort((want["dead_index"], want["dead_batch"]))
+    assert np.array_equal(sh.result["dead_index"][a], want["dead_index"][b])
+    assert np.array_equal(sh.result["dead"][:nd][a], want["dead"][:nd][b])
+    assert np.array_equal(sh.result["dead"][nd:], want["dead"][nd:])
+    np.testing.assert_allclose(sh.result["logZ"], want["logZ"], rtol=1e-13)
+    np.testing.assert_allclose(sh.result["information"], want["information"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_global_selection_and_redundant_accumulation(world):
+    """Every step: the union of what the ranks kill is exactly the global k worst of the whole
+    live set (np.argmin order over global indices); all ranks hold identical accumulators."""
+    n, k, deaths = 120, 12, 300
+    shards = _shards(world, n, k)
+    comm = LocalComm(world)
+    for sh in shards:
+        sh.init()
+    done = 0
+    while done < deaths:
+        kk = min(k, deaths - done)
+        glob = np.concatenate([sh.logl for sh in shards])
+        expect = set(select_k_worst(glob, kk).tolist())
+        gathered = comm.all_gather([sh.candidates(kk) for sh in shards])
+        for sh, r in zip(shards, comm.ranks):
+            sh.commit(gathered, world, r, kk)
+        got = set()
+        for sh in shards:
+            got |= set((np.asarray(sh.last_dead) + sh.row_offset).tolist())
+        assert got == expect
+        assert len({(sh.logX, sh.acc.Z, sh.acc.M, sh.acc.Zs, sh.lstar) for sh in shards}) == 1
+        done += kk
+        if done < deaths:
+            for sh in shards:
+                sh.refill()
+    partials = comm.all_gather([sh.final_partial() for sh in shards])
+    res = [sh.finalize_sharded(partials, world, r) for sh, r in zip(shards, comm.ranks)]
+    assert len({(r_["logZ"], r_["information"]) for r_ in res}) == 1
+    rows = np.concatenate([r_["dead"] for r_ in res])
+    assert rows.shape[0] == deaths + (n - (deaths % k or k))
+    assert abs(rows[:, 1].sum() - 1.0) < 1e-12              # all prior mass accounted for across ranks
+    assert abs(res[0]["logZ"] - (-4.6052)) < 0.6
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n, k, deaths, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    off, n_loc = shard_bounds(n, world, rank)
+    sh = OracleShard(TABLE, Model("iid_gaussian", 2), n_loc, batch_k=k, row_offset=off, global_population=n, **KW)
+    run_sharded([sh], TorchDistComm(), deaths, k)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), dead=sh.result["dead"], idx=sh.result["dead_index"],
+             logZ=sh.result["logZ"], info=sh.result["information"])
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_matches_in_process_emulation(tmp_path):
+    import torch.multiprocessing as mp
+    n, k, deaths, world = 80, 8, 200, 2
+    mp.spawn(_gloo_worker, args=(world, _free_port(), n, k, deaths, str(tmp_path)), nprocs=world, join=True)
+    shards = _shards(world, n, k)
+    run_sharded(shards, LocalComm(world), deaths, k)
+    for r, sh in enumerate(shards):
+        got = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(got["dead"], sh.result["dead"])
+        assert np.array_equal(got["idx"], sh.result["dead_index"])
+        assert float(got["logZ"]) == sh.result["logZ"] and float(got["info"]) == sh.result["information"]
