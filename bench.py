@@ -205,8 +205,8 @@ def run_b200_arm(args):
     N = w["population"] * world            # weak scaling: 10^4 live points per GPU, one global run
     k = args.batch_k if args.batch_k else N // 10
     n_deaths = death_count(N, w["cutoff"])
-    from gleipnir_b200.sharded import TorchDistComm, run_sharded, shard_bounds
-    comm = TorchDistComm() if world > 1 else None
+    from gleipnir_b200.sharded import get_nccl_comm, run_sharded_native, shard_bounds
+    comm = get_nccl_comm() if world > 1 else None
     table = [(L.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
     like = EggCartonLogLikelihood(d)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")     # > 126 MB L2
@@ -232,7 +232,7 @@ def run_b200_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if world > 1:
-            run_sharded([eng], comm, n_deaths, k)
+            run_sharded_native(eng, comm, n_deaths, k)
         else:
             eng.init()
             eng.advance(n_deaths)
@@ -247,6 +247,8 @@ def run_b200_arm(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)                    # let nvidia-smi deliver its first samples
+    barrier()                              # (rank 0 slept: re-align the ranks before timing)
     times, evals, launches, logzs, errs = [], 0, 0, [], []
     walk_ms = walk_launches = sel_ms = sel_launches = 0
     t_wall0 = time.perf_counter()
@@ -263,7 +265,6 @@ def run_b200_arm(args):
         last_rows = int(st.n_rows)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end through the public API (host in, host out) -----------------------------
     from scipy.stats import uniform
@@ -291,6 +292,7 @@ def run_b200_arm(args):
         e2e_t += t
         e2e_evals += ns._n_evals / world           # sharded runs report the global count on every rank
     barrier()
+    clk = clocks.stop() if rank == 0 else None      # sampled over both timed regions
 
     # max over ranks (device time), sum of evals over ranks
     dev_t = torch.tensor([sum(times) * 1e-3, e2e_t], dtype=torch.float64, device="cuda")
@@ -326,7 +328,8 @@ def run_b200_arm(args):
                     avg_launch_us=avg_launch_s * 1e6, launches_timed=int(walk_launches),
                     walker_share_of_step=walk_ms / (sum(times)), select_share_of_step=sel_ms / (sum(times)),
                     select_avg_launch_us=1e3 * sel_ms / max(sel_launches, 1),
-                    select_hbm=dict(bound="hbm", achieved=(8.0 * N) / (1e-3 * sel_ms / max(sel_launches, 1)) / 1e9,
+                    select_hbm=dict(bound="hbm", achieved=((8.0 * N / world) / (1e-3 * sel_ms / sel_launches) / 1e9)
+                                    if sel_ms > 0 and sel_launches else None,
                                     peak=peaks.get("hbm_gbs"), unit="GB/s"))
     # ---- CPU baseline: bounded sample on one host core ---------------------------------------
     # init (N rvs + N logL) and the per-iteration sampler cost are timed separately so that the

@@ -89,6 +89,13 @@ _SIGNATURES = {
     "gl_ns_shard_commit": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     "gl_ns_shard_final_partial": (c_int, [_P, _P, _P]),
     "gl_ns_shard_finalize": (c_int, [_P, _P, c_int32, c_int32, _P]),
+    "gl_comm_unique_id_bytes": (c_int, []),
+    "gl_comm_unique_id": (c_int, [_P]),
+    "gl_comm_create": (c_int, [c_int32, c_int32, _P, POINTER(_P)]),
+    "gl_comm_destroy": (c_int, [_P]),
+    "gl_comm_all_gather_f64": (c_int, [_P, _P, _P, c_int64, _P]),
+    "gl_ns_advance_sharded": (c_int, [_P, _P, c_int64, c_int32, c_int64, _P]),
+    "gl_ns_finalize_sharded": (c_int, [_P, _P, _P]),
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),

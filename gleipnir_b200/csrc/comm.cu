@@ -1,0 +1,181 @@
+// NCCL plumbing for the sharded run: one rank per process/GPU, the only data-path
+// collective is an all-gather of k doubles per rank per step (global likelihood threshold L*)
+// plus one of 4 doubles per rank for the final live-point term.  The collective is enqueued on
+// the SAME stream as the engine's kernels, from the same C++ loop, so a whole sharded run is
+// enqueued without host round trips.
+//
+// libnccl is resolved lazily with dlopen/dlsym: the library carries no link-time NCCL dependency
+// and single-GPU use never touches it.  Inside a PyTorch process "libnccl.so.2" resolves to the
+// copy torch already loaded.
+#include <dlfcn.h>
+#include <nccl.h>
+#include "common.cuh"
+
+struct gl_comm {
+    ncclComm_t comm;
+    int world, rank;
+    double *send;        // [cap]        this rank's candidates / partials
+    double *recv;        // [world*cap]  gathered
+    size_t cap;
+};
+
+namespace gl {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi &nccl() {
+    static NcclApi api;
+    return api;
+}
+
+static int nccl_load() {
+    NcclApi &a = nccl();
+    if (a.handle) return GL_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) {
+        set_error("cannot load libnccl (%s)", dlerror());
+        return GL_ECUDA;
+    }
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString) {
+        set_error("libnccl lacks a required symbol");
+        a.handle = nullptr;
+        return GL_ECUDA;
+    }
+    return GL_OK;
+}
+
+static int nccl_fail(ncclResult_t r, const char *what) {
+    set_error("NCCL error %d (%s) in %s", (int)r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", what);
+    return GL_ECUDA;
+}
+
+#define GL_NCCL(call)                                              \
+    do {                                                           \
+        ncclResult_t r__ = (call);                                 \
+        if (r__ != ncclSuccess) return gl::nccl_fail(r__, #call);  \
+    } while (0)
+
+int comm_reserve(gl_comm *c, size_t count) {
+    if (count <= c->cap) return GL_OK;
+    if (c->send) cudaFree(c->send);
+    if (c->recv) cudaFree(c->recv);
+    c->send = c->recv = nullptr;
+    GL_CUDA(cudaMalloc(&c->send, sizeof(double) * count));
+    GL_CUDA(cudaMalloc(&c->recv, sizeof(double) * count * (size_t)c->world));
+    c->cap = count;
+    return GL_OK;
+}
+
+int comm_all_gather(gl_comm *c, const double *send, double *recv, size_t count, cudaStream_t st) {
+    GL_NCCL(nccl().AllGather(send, recv, count, ncclDouble, c->comm, st));
+    return GL_OK;
+}
+
+}  // namespace gl
+
+extern "C" {
+
+int gl_comm_unique_id_bytes(void) { return (int)sizeof(ncclUniqueId); }
+
+int gl_comm_unique_id(uint8_t *out_bytes) {
+    GL_REQUIRE(out_bytes != nullptr, "out is NULL");
+    int rc = gl::nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    GL_NCCL(gl::nccl().GetUniqueId(&id));
+    memcpy(out_bytes, &id, sizeof(id));
+    return GL_OK;
+}
+
+int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, gl_comm **out) {
+    GL_REQUIRE(out != nullptr && id_bytes != nullptr, "NULL argument");
+    GL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad world/rank");
+    int rc = gl::nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    gl_comm *c = new gl_comm();
+    c->world = world;
+    c->rank = rank;
+    c->send = c->recv = nullptr;
+    c->cap = 0;
+    ncclResult_t r = gl::nccl().CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return gl::nccl_fail(r, "ncclCommInitRank");
+    }
+    *out = c;
+    return GL_OK;
+}
+
+int gl_comm_destroy(gl_comm *c) {
+    if (!c) return GL_OK;
+    if (c->send) cudaFree(c->send);
+    if (c->recv) cudaFree(c->recv);
+    if (c->comm) gl::nccl().CommDestroy(c->comm);
+    delete c;
+    return GL_OK;
+}
+
+int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream) {
+    GL_REQUIRE(c != nullptr && send_dev != nullptr && recv_dev != nullptr && count >= 1, "bad argument");
+    return gl::comm_all_gather(c, send_dev, recv_dev, (size_t)count, (cudaStream_t)stream);
+}
+
+// Enqueue the sharded run until `n_deaths_total` GLOBAL deaths: per step candidates -> NCCL
+// all-gather -> commit -> refill, all on `stream`.
+int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
+                          void *stream) {
+    GL_REQUIRE(ns != nullptr && c != nullptr, "NULL argument");
+    GL_REQUIRE(batch_k >= 1, "batch_k must be >= 1");
+    int rc = gl::comm_reserve(c, (size_t)(batch_k > 4 ? batch_k : 4));
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t done = n_dead_so_far;
+    bool first = true;
+    while (done < n_deaths_total) {
+        const int32_t k = (int32_t)((n_deaths_total - done) < batch_k ? (n_deaths_total - done) : batch_k);
+        if (!first || n_dead_so_far > 0) {
+            rc = gl_ns_refill(ns, stream);
+            if (rc) return rc;
+        }
+        first = false;
+        rc = gl_ns_shard_candidates(ns, k, c->send, stream);
+        if (rc) return rc;
+        rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)k, st);
+        if (rc) return rc;
+        rc = gl_ns_shard_commit(ns, c->recv, c->world, c->rank, k, stream);
+        if (rc) return rc;
+        done += k;
+    }
+    return GL_OK;
+}
+
+int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream) {
+    GL_REQUIRE(ns != nullptr && c != nullptr, "NULL argument");
+    int rc = gl::comm_reserve(c, 4);
+    if (rc) return rc;
+    rc = gl_ns_shard_final_partial(ns, c->send, stream);
+    if (rc) return rc;
+    rc = gl::comm_all_gather(c, c->send, c->recv, 4, (cudaStream_t)stream);
+    if (rc) return rc;
+    return gl_ns_shard_finalize(ns, c->recv, c->world, c->rank, stream);
+}
+
+}  // extern "C"

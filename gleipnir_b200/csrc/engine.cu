@@ -174,30 +174,15 @@ __global__ void __launch_bounds__(256) shard_local_kernel(EngineState *S, const 
 constexpr int KILL_SMALL_THREADS = 1024;
 constexpr int KILL_SMALL_MAX_N = 24 * 1024;      // 192 KB of keys + 8 KB histogram + scratch
 
-__global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
-    EngineState *S, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
-    long long capacity, const double *__restrict__ live, const double *__restrict__ logl,
-    long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, double *__restrict__ dead_x,
-    double *__restrict__ dead_logl, double *__restrict__ dead_w, long long *__restrict__ dead_idx,
-    int *__restrict__ dead_step) {
-    extern __shared__ unsigned long long keys[];                 // [N]
-    __shared__ unsigned int hist[SEL_BINS];
-    __shared__ double scratch[33];
+// Single-CTA (1024 threads) selection of the k smallest of keys[0..N) -- ordering keys held in
+// shared memory -- under (key, index) order.  Writes the selected indices in ascending order to
+// out_list[0..k), optionally flags them in is_dead, and returns the largest selected key to
+// every thread.  `hist` is 2048 words of shared scratch.
+__device__ unsigned long long cta_select_kworst(const unsigned long long *keys, int N, int k, unsigned int *hist,
+                                                long long *__restrict__ dead_list,
+                                                unsigned char *__restrict__ is_dead) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = KILL_SMALL_THREADS / 32;
-
-    // ---- begin: batch size -------------------------------------------------------------------
-    long long kk = n_target - S->n_dead;
-    if (kk > k_req) kk = k_req;
-    if (kk > N - 1) kk = N - 1;
-    if (kk < 0) kk = 0;
-    const int k = (int)kk;
-    if (tid == 0) { S->k_cur = k; S->do_walk = 0; }
-    if (k <= 0) return;
-
-    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
-    __syncthreads();
-
     // ---- radix select on 4-bit digits, NO atomics ------------------------------------------------
     // (1) min/max key -> the leading nibbles they share are skipped; (2) per pass each thread counts
     // its candidates' digits in two 64-bit words of 8-bit counters (<= 24 keys per thread), widened
@@ -310,7 +295,7 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
         if (is_lt || (is_eq && eq_before < r)) {
             const int pos = lt_before + (eq_before < r ? eq_before : r);
             dead_list[pos] = i;
-            is_dead[i] = 1;
+            if (is_dead) is_dead[i] = 1;
             kstar = key > kstar ? key : kstar;
         }
         run_lt += __popc(b_lt);
@@ -328,6 +313,35 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
         const unsigned long long a = mm[w];
         kstar = a > kstar ? a : kstar;
     }
+
+    return kstar;
+}
+
+__global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
+    EngineState *S, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
+    long long capacity, const double *__restrict__ live, const double *__restrict__ logl,
+    long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, double *__restrict__ dead_x,
+    double *__restrict__ dead_logl, double *__restrict__ dead_w, long long *__restrict__ dead_idx,
+    int *__restrict__ dead_step) {
+    extern __shared__ unsigned long long keys[];                 // [N]
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ double scratch[33];
+    const int tid = threadIdx.x;
+
+    // ---- begin: batch size -------------------------------------------------------------------
+    long long kk = n_target - S->n_dead;
+    if (kk > k_req) kk = k_req;
+    if (kk > N - 1) kk = N - 1;
+    if (kk < 0) kk = 0;
+    const int k = (int)kk;
+    if (tid == 0) { S->k_cur = k; S->do_walk = 0; }
+    if (k <= 0) return;
+
+    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
+    __syncthreads();
+
+    const unsigned long long kstar = cta_select_kworst(keys, N, k, hist, dead_list, is_dead);
+    __syncthreads();
 
     // ---- record (nested_sampling.py:130-133,170-173) --------------------------------------------
     const long long base_row = S->n_rows;
@@ -390,6 +404,118 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
         if (room) S->n_rows += k;
         S->lstar = key_to_double(kstar);
         S->do_walk = S->n_dead < n_target;
+    }
+}
+
+// ---- fused single-CTA kernels of the sharded step (local N and world*k both <= KILL_SMALL_MAX_N) --
+// candidates: this rank's k worst slots (ascending slot order) and their logL, one launch
+__global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_candidates_small_kernel(
+    const double *__restrict__ logl, int N, int k, long long *__restrict__ cand_list, double *__restrict__ cand_logl) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ unsigned int hist[SEL_BINS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
+    __syncthreads();
+    (void)cta_select_kworst(keys, N, k, hist, cand_list, nullptr);
+    __syncthreads();
+    for (int i = tid; i < k; i += KILL_SMALL_THREADS) cand_logl[i] = logl[cand_list[i]];
+}
+
+// commit: global selection over the gathered [world*k] candidates, translation of this rank's
+// share to local slots, dead-row record and the (redundant, identical on every rank) evidence
+// update -- one launch.  Same forms as shard_local_kernel + record_kernel + accumulate_kernel.
+__global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
+    EngineState *S, const double *__restrict__ gathered, int world, int rank, int k, int d, long long row_offset,
+    double n_global, long long capacity, const long long *__restrict__ cand_list, long long *__restrict__ positions,
+    const double *__restrict__ live, const double *__restrict__ logl, long long *__restrict__ dead_list,
+    unsigned char *__restrict__ is_dead, double *__restrict__ dead_x, double *__restrict__ dead_logl,
+    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ double scratch[33];
+    __shared__ int s_start, s_end;
+    const int tid = threadIdx.x;
+    const int n = world * k;
+    for (int i = tid; i < n; i += KILL_SMALL_THREADS) keys[i] = sort_key(gathered[i]);
+    __syncthreads();
+    const unsigned long long kstar = cta_select_kworst(keys, n, k, hist, positions, nullptr);
+    __syncthreads();
+    if (tid == 0) {
+        const long long lo_pos = (long long)rank * k, hi_pos = lo_pos + k;
+        int a = 0, b = k;
+        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < lo_pos) a = m + 1; else b = m; }
+        s_start = a;
+        b = k;
+        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < hi_pos) a = m + 1; else b = m; }
+        s_end = a;
+    }
+    __syncthreads();
+    const int start = s_start, n_loc = s_end - s_start;
+    for (int i = tid; i < n_loc; i += KILL_SMALL_THREADS) {
+        const long long slot = cand_list[positions[start + i] - (long long)rank * k];
+        dead_list[i] = slot;
+        is_dead[slot] = 1;
+    }
+    __syncthreads();
+    const long long base_row = S->n_rows;
+    const double logw = S->logX - log(n_global + 1.0);
+    const double w = exp(logw);
+    const bool room = base_row + n_loc <= capacity;
+    if (room) {
+        const int step = S->step;
+        for (int e = tid; e < n_loc * d; e += KILL_SMALL_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const long long slot = dead_list[q];
+            dead_x[(base_row + q) * d + j] = live[slot * d + j];
+            if (j == 0) {
+                dead_logl[base_row + q] = logl[slot];
+                dead_w[base_row + q] = w;
+                dead_idx[base_row + q] = slot + row_offset;
+                dead_step[base_row + q] = step;
+            }
+        }
+    }
+    double mx = -INFINITY;
+    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
+        const double lw = logw + gathered[positions[i]];
+        if (isfinite(lw)) mx = fmax(mx, lw);
+    }
+    mx = block_max(mx, scratch);
+    const double m_old = S->M;
+    const double m_new = fmax(m_old, mx);
+    double sz = 0.0, sh = 0.0, zl = 0.0, hl = 0.0;
+    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
+        const double L = gathered[positions[i]];
+        const double lw = logw + L;
+        if (isfinite(lw)) {
+            const double t = exp(lw - m_new);
+            sz += t;
+            sh += t * L;
+        }
+        const double dZ = w * exp(L);
+        zl += dZ;
+        const double dH = dZ * L;
+        if (dH == dH) hl += dH;
+    }
+    sz = block_sum(sz, scratch);
+    sh = block_sum(sh, scratch);
+    zl = block_sum(zl, scratch);
+    hl = block_sum(hl, scratch);
+    if (tid == 0) {
+        if (mx > -INFINITY) {
+            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+            S->Zs = S->Zs * scale + sz;
+            S->Hs = S->Hs * scale + sh;
+            S->M = m_new;
+        }
+        S->Z_lin += zl;
+        S->H_lin += hl;
+        S->logX += log((n_global - (double)k + 1.0) / (n_global + 1.0));
+        S->n_dead += k;
+        if (room) S->n_rows += n_loc;
+        S->lstar = key_to_double(kstar);
+        S->k_cur = n_loc;
+        S->do_walk = 1;
     }
 }
 
@@ -696,6 +822,13 @@ static int blocks_for(long long items, int threads, int cap_per_sm) {
     return (int)b;
 }
 
+// opt a kernel into > 48 KB of dynamic shared memory (idempotent; raises the limit to the device max once)
+static int ensure_smem(const void *fn, int bytes) {
+    if (bytes <= 40 * 1024) return GL_OK;
+    GL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return GL_OK;
+}
+
 static void prof_mark(gl_ns *ns, std::vector<cudaEvent_t> &v, cudaStream_t st) {
     if (!ns->prof || v.size() >= 16384) return;
     cudaEvent_t e;
@@ -709,11 +842,8 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
     const double n_global = (double)ns->cfg.global_population;
     if (N <= KILL_SMALL_MAX_N && !ns->force_multipass) {
         const int smem = (int)(sizeof(unsigned long long) * N);
-        static thread_local int configured = 0;
-        if (smem > 40 * 1024 && smem > configured) {
-            GL_CUDA(cudaFuncSetAttribute(kill_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = smem;
-        }
+        int rc0 = ensure_smem((const void *)kill_small_kernel, smem);
+        if (rc0) return rc0;
         prof_mark(ns, ns->ev_sel, st);
         kill_small_kernel<<<1, KILL_SMALL_THREADS, smem, st>>>(
             ns->S, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
@@ -1008,9 +1138,23 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
     }
     GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k && k < ns->cfg.population_size, "k=%d outside [1, min(batch_k, N_local-1)]", k);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = gl::select_launch(ns->buf.logl, ns->cfg.population_size, nullptr, k, 0, ns->cand_list, nullptr, nullptr,
-                               ns->sel, st);
+    const long long N = ns->cfg.population_size;
+    gl::prof_mark(ns, ns->ev_sel, st);
+    if (N <= gl::KILL_SMALL_MAX_N && !ns->force_multipass) {
+        int rc = gl::ensure_smem((const void *)gl::shard_candidates_small_kernel, (int)(8 * N));
+        if (rc) return rc;
+        gl::shard_candidates_small_kernel<<<1, gl::KILL_SMALL_THREADS, (int)(8 * N), st>>>(ns->buf.logl, (int)N, k,
+                                                                                          ns->cand_list, cand_logl_dev);
+        GL_CHECK_LAUNCH();
+        gl::prof_mark(ns, ns->ev_sel, st);
+        ns->prof_sel_launches += 1;
+        ns->h_launches += 1;
+        return GL_OK;
+    }
+    int rc = gl::select_launch(ns->buf.logl, N, nullptr, k, 0, ns->cand_list, nullptr, nullptr, ns->sel, st);
     if (rc) return rc;
+    gl::prof_mark(ns, ns->ev_sel, st);
+    ns->prof_sel_launches += gl::SEL_PASSES + 2;
     gl::shard_gather_kernel<<<gl::blocks_for(k, 256, 4), 256, 0, st>>>(ns->cand_list, ns->buf.logl, k, cand_logl_dev);
     GL_CHECK_LAUNCH();
     ns->h_launches += gl::SEL_PASSES + 2 + 1;
@@ -1024,6 +1168,21 @@ int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world
     GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k, "k=%d outside [1, batch_k]", k);
     cudaStream_t st = (cudaStream_t)stream;
     const double n_global = (double)ns->cfg.global_population;
+    if ((long long)world * k <= gl::KILL_SMALL_MAX_N && !ns->force_multipass) {
+        const int smem = 8 * world * k;
+        int rc0 = gl::ensure_smem((const void *)gl::shard_commit_small_kernel, smem);
+        if (rc0) return rc0;
+        gl::shard_commit_small_kernel<<<1, gl::KILL_SMALL_THREADS, smem, st>>>(
+            ns->S, gathered_logl_dev, world, rank, k, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
+            ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
+            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+        GL_CHECK_LAUNCH();
+        ns->h_launches += 1;
+        ns->h_n_dead += k;
+        ns->h_k_last = -1;
+        ns->pending_refill = true;
+        return GL_OK;
+    }
     int rc = gl::select_launch(gathered_logl_dev, (long long)world * k, nullptr, k, 0, ns->positions, nullptr, nullptr,
                                ns->sel2, st);
     if (rc) return rc;

@@ -105,9 +105,9 @@ class NestedSampling(NestedSamplingBase):
     def _run_sharded(self, dist, loglike, table, n, k, seed, scfg, n_deaths, verbose):
         """One shard per rank, global threshold by all-gather (gleipnir_b200/sharded.py)."""
         import torch
-        from ..sharded import TorchDistComm, run_sharded, shard_bounds
-        comm = TorchDistComm()
-        rank = comm.ranks[0]
+        from ..sharded import gather_dead_tables, get_nccl_comm, run_sharded_native, shard_bounds
+        comm = get_nccl_comm()
+        rank = comm.rank
         seed_t = torch.tensor([seed], dtype=torch.int64, device="cuda")
         dist.broadcast(seed_t, 0)                       # every rank must use rank 0's Philox key
         off, n_loc = shard_bounds(n, comm.world, rank)
@@ -116,21 +116,16 @@ class NestedSampling(NestedSamplingBase):
         eng = DeviceEngine(table, loglike.device_model(), n_loc, k, n_deaths, seed=int(seed_t.item()),
                            device=self.device, row_offset=off, global_population=n, **scfg)
         self._engine = eng
-        run_sharded([eng], comm, n_deaths, k)
+        run_sharded_native(eng, comm, n_deaths, k)
         st = eng.state()
-        rows, idx, step = eng.dead_table()
-        parts = [None] * comm.world
-        dist.all_gather_object(parts, (rows, idx, step))
-        rows = np.concatenate([p[0] for p in parts])
-        idx = np.concatenate([p[1] for p in parts])
-        step = np.concatenate([p[2] for p in parts])
+        rows, idx, step = gather_dead_tables(eng)
         from ..engine import death_order
         order = death_order(rows[:, 0], idx, step)
         evals = torch.tensor([st.n_evals], dtype=torch.int64, device="cuda")
         dist.all_reduce(evals)
-        live = [None] * comm.world
-        dist.all_gather_object(live, eng.live.cpu().numpy())
-        return st, rows[order], int(evals.item()), np.concatenate(live)
+        live = torch.empty((n, eng.d), dtype=torch.float64, device=eng.device)
+        dist.all_gather_into_tensor(live, eng.live)
+        return st, rows[order], int(evals.item()), live.cpu().numpy()
 
     def run(self, verbose=False):
         loglike = require_device_loglikelihood(self.loglikelihood)

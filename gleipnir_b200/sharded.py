@@ -81,3 +81,81 @@ def run_sharded(shards, comm, n_deaths, batch_k, init=True):
     for sh, r in zip(shards, comm.ranks):
         sh.finalize_sharded(partials, comm.world, r)
     return done
+
+
+class NcclComm(object):
+    """Native communicator (``gl_comm``): NCCL called from the library's own C++ loop, on the
+    engine's stream.  The NCCL unique id is created on rank 0 and broadcast with
+    torch.distributed (plumbing); ``gl_comm_create`` is collective."""
+
+    def __init__(self, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import _lib
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = self.lib.gl_comm_unique_id_bytes()
+        buf = (ctypes.c_uint8 * nbytes)()
+        if self.rank == 0:
+            _lib.check(self.lib.gl_comm_unique_id(buf))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (ctypes.c_uint8 * nbytes).from_buffer_copy(box[0])
+        self.h = ctypes.c_void_p()
+        _lib.check(self.lib.gl_comm_create(self.world, self.rank, ident, ctypes.byref(self.h)))
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            self.lib.gl_comm_destroy(h)
+            self.h = None
+
+
+_comm_cache = {}
+
+
+def get_nccl_comm(group=None):
+    """One native communicator per process group (creating one costs a NCCL bootstrap)."""
+    key = id(group)
+    if key not in _comm_cache:
+        _comm_cache[key] = NcclComm(group)
+    return _comm_cache[key]
+
+
+def gather_dead_tables(engine, group=None):
+    """All ranks' dead-point logs on every rank: (rows [n, d+2], slot idx, step), unsorted.
+    One padded tensor all-gather over NCCL instead of pickled objects."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rows = int(engine.state().n_rows)
+    d = engine.d
+    counts = torch.zeros(world, dtype=torch.int64, device=engine.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([rows], dtype=torch.int64, device=engine.device), group=group)
+    counts = counts.cpu().numpy()
+    mx = int(counts.max())
+    mine = torch.zeros((mx, d + 4), dtype=torch.float64, device=engine.device)
+    mine[:rows, 0] = engine.dead_logl[:rows]
+    mine[:rows, 1] = engine.dead_w[:rows]
+    mine[:rows, 2:2 + d] = engine.dead_x[:rows]
+    mine[:rows, 2 + d] = engine.dead_idx[:rows].to(torch.float64)        # exact below 2^53
+    mine[:rows, 3 + d] = engine.dead_step[:rows].to(torch.float64)
+    allr = torch.empty((world * mx, d + 4), dtype=torch.float64, device=engine.device)
+    dist.all_gather_into_tensor(allr, mine, group=group)
+    allr = allr.cpu().numpy().reshape(world, mx, d + 4)
+    parts = [allr[r, :counts[r]] for r in range(world)]
+    cat = np.concatenate(parts)
+    return cat[:, :d + 2], cat[:, d + 2].astype(np.int64), cat[:, d + 3].astype(np.int64)
+
+
+def run_sharded_native(engine, nccl_comm, n_deaths, batch_k):
+    """Whole sharded run enqueued from C++ (gl_ns_advance_sharded / gl_ns_finalize_sharded)."""
+    from . import _lib
+    engine.init()
+    st = engine._stream()
+    _lib.check(engine.lib.gl_ns_advance_sharded(engine._h, nccl_comm.h, int(n_deaths), int(batch_k), 0, st))
+    _lib.check(engine.lib.gl_ns_finalize_sharded(engine._h, nccl_comm.h, st))

@@ -232,6 +232,21 @@ GL_API int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *strea
 GL_API int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank,
                                 void *stream);
 
+/* Native sharded loop: NCCL all-gathers enqueued on the engine's stream from C++ (libnccl is
+ * dlopen'ed on first use).  gl_comm_unique_id on rank 0 -> broadcast the bytes by any means
+ * (torch.distributed in the Python host) -> gl_comm_create on every rank (collective). */
+typedef struct gl_comm gl_comm;
+GL_API int gl_comm_unique_id_bytes(void);
+GL_API int gl_comm_unique_id(uint8_t *out_bytes);
+GL_API int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, gl_comm **out);
+GL_API int gl_comm_destroy(gl_comm *c);
+GL_API int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream);
+/* Enqueue steps (refill of the waiting batch, candidates, all-gather, commit) until
+ * `n_deaths_total` global deaths; `n_dead_so_far` = global deaths already recorded. */
+GL_API int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k,
+                                 int64_t n_dead_so_far, void *stream);
+GL_API int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream);
+
 /* Populations whose ordering keys fit in shared memory (N <= 24576) use a single-CTA fused
  * kill kernel; this switch forces the general multi-launch selection path (used by tests so
  * that both paths are checked against each other and the oracle). */
