@@ -657,6 +657,7 @@ __global__ void final_combine_kernel(EngineState *S, const double *partials, int
         if (b >= local_first && b < local_first + local_count) cnt_local += partials[4 * b + 3];
     }
     S->fin_n_local = (long long)cnt_local;
+    S->n_rows_dead = S->n_rows;
     if (cnt <= 0.0) return;
     const double X = exp(S->logX);
     const double lm = lin / cnt;                                  // mean likelihood (:187)
@@ -715,6 +716,79 @@ __global__ void final_done_kernel(EngineState *S, long long capacity) {
 }
 
 constexpr int FIN_MAX_BLOCKS = 1024;
+
+// ---- export: dead table [rows, d+2] in death order ---------------------------------------------
+// The log holds each batch in slot order; the reference's table is in death order (ascending
+// (logL, slot) inside a batch, survivors last in slot order; nested_sampling.py:130-133,195-203).
+// One CTA per batch sorts its (key, row) pairs with a bitonic network in shared memory and writes
+// the rows straight into the output table, so the export is one kernel + one D2H copy.
+constexpr int EXPORT_THREADS = 512;
+
+__global__ void __launch_bounds__(EXPORT_THREADS) export_batches_kernel(
+    const EngineState *S, const double *__restrict__ dead_x, const double *__restrict__ dead_logl,
+    const double *__restrict__ dead_w, const long long *__restrict__ dead_idx, const int *__restrict__ dead_step,
+    int d, int seg_cap /* power of two >= largest batch */, double *__restrict__ out) {
+    extern __shared__ unsigned long long sk[];                 // keys[seg_cap] | rows[seg_cap] (as u64)
+    unsigned long long *sr = sk + seg_cap;
+    const long long n_dead = S->finalized ? S->n_rows_dead : S->n_rows;
+    const long long n_rows = S->n_rows;
+    const int step = blockIdx.x;
+    // rows of this batch: [lo, hi) by binary search on the non-decreasing step column
+    long long lo = 0, hi = n_dead;
+    {
+        long long a = 0, b = n_dead;
+        while (a < b) { const long long m = (a + b) >> 1; if (dead_step[m] < step) a = m + 1; else b = m; }
+        lo = a;
+        b = n_dead;
+        while (a < b) { const long long m = (a + b) >> 1; if (dead_step[m] < step + 1) a = m + 1; else b = m; }
+        hi = a;
+    }
+    const int n = (int)(hi - lo);
+    if (n > 0 && n <= seg_cap) {
+        for (int i = threadIdx.x; i < seg_cap; i += EXPORT_THREADS) {
+            sk[i] = i < n ? sort_key(dead_logl[lo + i]) : ~0ull;
+            sr[i] = i < n ? (unsigned long long)dead_idx[lo + i] << 24 | (unsigned long long)i : ~0ull;
+        }
+        __syncthreads();
+        // bitonic sort on (key, slot) -- rows inside a batch are already in slot order, and the
+        // slot is carried in sr's high bits, so ties break by lowest slot
+        for (int size = 2; size <= seg_cap; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < seg_cap / 2; t += EXPORT_THREADS) {
+                    const int i = 2 * t - (t & (stride - 1));
+                    const int j = i + stride;
+                    const bool up = (i & size) == 0;
+                    const unsigned long long ki = sk[i], kj = sk[j], ri = sr[i], rj = sr[j];
+                    const bool gt = ki > kj || (ki == kj && ri > rj);
+                    if (gt == up) { sk[i] = kj; sk[j] = ki; sr[i] = rj; sr[j] = ri; }
+                }
+                __syncthreads();
+            }
+        }
+        for (long long e = threadIdx.x; e < (long long)n * (d + 2); e += EXPORT_THREADS) {
+            const int q = (int)(e / (d + 2)), c = (int)(e - (long long)q * (d + 2));
+            const long long src = lo + (long long)(sr[q] & 0xffffffull);
+            out[(lo + q) * (d + 2) + c] = c == 0 ? dead_logl[src] : c == 1 ? dead_w[src] : dead_x[src * d + (c - 2)];
+        }
+    } else if (n > seg_cap) {
+        // oversized batch: keep slot order (the host sorts such batches)
+        for (long long e = threadIdx.x; e < (long long)n * (d + 2); e += EXPORT_THREADS) {
+            const long long q = e / (d + 2);
+            const int c = (int)(e - q * (d + 2));
+            const long long src = lo + q;
+            out[src * (d + 2) + c] = c == 0 ? dead_logl[src] : c == 1 ? dead_w[src] : dead_x[src * d + (c - 2)];
+        }
+    }
+    // the last block also copies the survivor rows (already in slot order)
+    if (blockIdx.x == gridDim.x - 1) {
+        for (long long e = threadIdx.x; e < (n_rows - n_dead) * (d + 2); e += EXPORT_THREADS) {
+            const long long q = e / (d + 2);
+            const int c = (int)(e - q * (d + 2));
+            const long long src = n_dead + q;
+            out[src * (d + 2) + c] = c == 0 ? dead_logl[src] : c == 1 ? dead_w[src] : dead_x[src * d + (c - 2)];
+        }
+    }
+}
 
 }  // namespace gl
 
@@ -1091,6 +1165,24 @@ int gl_ns_finalize(gl_ns *ns, void *stream) {
     GL_CHECK_LAUNCH();
     ns->h_launches += 4;
     ns->finalized = true;
+    return GL_OK;
+}
+
+int gl_ns_export_dead(gl_ns *ns, double *table_dev, void *stream) {
+    GL_REQUIRE(ns != nullptr && table_dev != nullptr, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int seg = 2;
+    while (seg < ns->cfg.batch_k) seg <<= 1;
+    if (seg > 8192) seg = 8192;                    // 128 KB of (key, row) pairs
+    const int smem = seg * 16;
+    int rc = gl::ensure_smem((const void *)gl::export_batches_kernel, smem);
+    if (rc) return rc;
+    const int n_steps = ns->h_step + 1;            // batches recorded (the last one is never refilled)
+    gl::export_batches_kernel<<<n_steps, gl::EXPORT_THREADS, smem, st>>>(
+        ns->S, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w, (const long long *)ns->buf.dead_idx,
+        ns->buf.dead_step, ns->d, seg, table_dev);
+    GL_CHECK_LAUNCH();
+    ns->h_launches += 1;
     return GL_OK;
 }
 

@@ -25,6 +25,7 @@ struct EngineState {                 // one instance in device memory per engine
     double fin_m, fin_s, fin_lin;
     long long fin_n;                 // survivors over ALL ranks (weight denominator)
     long long fin_n_local;           // survivors of this engine (rows it appends)
+    long long n_rows_dead;           // rows recorded by deaths (before the survivor rows)
     unsigned long long n_evals;      // log-likelihood evaluations performed by this engine
 };
 

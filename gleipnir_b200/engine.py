@@ -135,6 +135,17 @@ class DeviceEngine(object):
         _lib.check(self.lib.gl_ns_read_state(self._h, ctypes.byref(st), self._stream()))
         return st
 
+    def dead_table_device(self):
+        """`dead_points` values assembled and ordered on the device (gl_ns_export_dead):
+        host array [rows, d+2] in death order after ONE device->host copy.  Batches larger than
+        8192 rows are left in slot order by the kernel; use dead_table() for those."""
+        torch = _torch()
+        st = self.state()
+        rows = int(st.n_rows)
+        table = torch.empty((rows, self.d + 2), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gl_ns_export_dead(self._h, table.data_ptr(), self._stream()))
+        return table.cpu().numpy()
+
     def dead_table(self):
         """Dead-point log as a host array [rows, d+2] (log_l, weight, x...) in death order,
         plus the slot index and batch id of every row."""

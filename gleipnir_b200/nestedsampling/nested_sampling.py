@@ -185,7 +185,10 @@ class NestedSampling(NestedSamplingBase):
                     break
         eng.finalize()
         st = eng.state()
-        table_rows, _idx, _step = eng.dead_table()
+        if k <= 8192:
+            table_rows = eng.dead_table_device()       # ordered on the device, one D2H copy
+        else:
+            table_rows, _idx, _step = eng.dead_table()
         return self._publish(st, table_rows, int(st.n_evals), eng.live.cpu().numpy(), n)
 
     def _publish(self, st, table_rows, n_evals, live, n):

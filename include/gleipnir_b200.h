@@ -208,6 +208,12 @@ GL_API int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_
  * dead buffers in index order with weight X/(#survivors). */
 GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 
+/* `dead_points` (nested_sampling.py:211,338-344) assembled on the device: table_dev[n_rows, d+2]
+ * (log_l, weight, x_0..x_{d-1}) in death order -- batches in sequence, ascending (logL, slot)
+ * inside a batch (sorted per batch in shared memory; batches larger than 8192 keep slot order),
+ * survivors last.  One kernel; the caller copies the table to the host. */
+GL_API int gl_ns_export_dead(gl_ns *ns, double *table_dev, void *stream);
+
 /* Copy the device state to the host (synchronises `stream`). */
 GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
 

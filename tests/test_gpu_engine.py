@@ -46,6 +46,7 @@ def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name, multip
     eng.finalize()
     st = eng.state()
     table, idx, step = eng.dead_table()
+    assert np.array_equal(eng.dead_table_device(), table, equal_nan=True)
     ref = g[name + "/dead"]
     cols = [0] + list(range(2, 2 + d))
     assert table.shape == ref.shape
@@ -141,6 +142,7 @@ def test_whole_run_matches_oracle_engine(cuda, case, multipass):
     np.testing.assert_allclose(st.information, want["information"], rtol=1e-10)
     np.testing.assert_allclose(np.array(st.widths[:d]), want["widths"], rtol=RTOL)
     assert st.n_dead == n_deaths and st.n_evals == want["n_evals"]
+    assert np.array_equal(eng.dead_table_device(), tab)          # device-side death-order export
 
 
 def test_run_host_entry_point_matches_device_api(cuda):
