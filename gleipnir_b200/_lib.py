@@ -67,6 +67,7 @@ _SIGNATURES = {
     "gl_model_create_mixture1d": (c_int, [POINTER(c_double), c_int32, c_double, POINTER(_P)]),
     "gl_model_create_dense_gaussian": (c_int, [c_int32, POINTER(c_double), POINTER(c_double), c_double, POINTER(_P)]),
     "gl_model_create_external": (c_int, [c_int32, _P, _P, _P, c_int64, POINTER(_P)]),
+    "gl_model_set_tensor_path": (c_int, [_P, c_int32]),
     "gl_model_dim": (c_int, [_P]),
     "gl_model_kind_of": (c_int, [_P]),
     "gl_model_destroy": (c_int, [_P]),
@@ -100,6 +101,7 @@ _SIGNATURES = {
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
+    "gl_microbench_dmma": (c_int, [c_int32, c_int32, _P, POINTER(c_int64), _P]),
     "gl_microbench_dfma": (c_int, [c_int32, c_int32, _P, POINTER(c_int64), _P]),
     "gl_ns_run_host": (c_int, [POINTER(gl_ns_config), POINTER(gl_prior), c_int32, _P, c_int64, POINTER(c_double),
                                POINTER(gl_ns_state)]),

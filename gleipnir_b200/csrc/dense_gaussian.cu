@@ -1,0 +1,139 @@
+// Dense correlated Gaussian, batched full quadratic form on the FP64 tensor cores (DMMA):
+//     logL_i = -0.5 (x_i - mu)^T P (x_i - mu) + log_norm          
+// tcgen05/UMMA has no FP64 type, so the sm_100a FP64 tensor path is mma.sync.m8n8k4.f64.
+// One warp owns 8 rows at a time: the 8 x d tile of residuals R is staged in shared memory
+// (rows are contiguous in HBM, so the load is fully coalesced), Y = R P is accumulated tile by
+// tile with DMMA (A = R fragments held in registers, B = P pre-arranged in fragment order in
+// shared memory, loaded once per CTA), and the row dot q_i = sum_j R_ij Y_ij is folded into the
+// accumulator read-out, so Y never leaves registers.
+// Algorithmic work: 2d^2 + 2d flop and 8d + 8 B per point (12.5 flop/B at d = 50).
+#include "common.cuh"
+#include "likelihoods.cuh"
+
+namespace gl {
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int DG_WARPS = 8;
+
+// Pf[(ks*NT + nt)*32 + lane] = P[ks*4 + (lane&3)][nt*8 + (lane>>2)]   (B fragment order)
+__global__ void dense_gaussian_pack_kernel(const double *__restrict__ P, int d, int KT, int NT,
+                                           double *__restrict__ Pf) {
+    const int total = KT * NT * 32;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int lane = e & 31, tile = e >> 5;
+        const int ks = tile / NT, nt = tile - ks * NT;
+        const int r = ks * 4 + (lane & 3), c = nt * 8 + (lane >> 2);
+        Pf[e] = (r < d && c < d) ? P[(size_t)r * d + c] : 0.0;
+    }
+}
+
+template <int KTM>
+__global__ void __launch_bounds__(DG_WARPS * 32) dense_gaussian_dmma_kernel(
+    const double *__restrict__ x, long long n, int d, int KT, int NT, const double *__restrict__ mu,
+    const double *__restrict__ Pf, double log_norm, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;          // padded row length
+    double *Ps = sm;                                           // [KT*NT*32]
+    double *Rs_all = Ps + (size_t)KT * NT * 32;                // [DG_WARPS][8][dp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < KT * NT * 32; e += DG_WARPS * 32) Ps[e] = Pf[e];
+    __syncthreads();
+    double *Rs = Rs_all + (size_t)warp * 8 * dp;
+    const int grp = lane >> 2, tig = lane & 3;
+    const long long n_tiles = (n + 7) / 8;
+    for (long long t = (long long)blockIdx.x * DG_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * DG_WARPS) {
+        const long long r0 = t * 8;
+        const int rows = (int)((n - r0) < 8 ? (n - r0) : 8);
+        // stage the residual tile (coalesced: rows*d contiguous doubles), zero padding
+        for (int e = lane; e < 8 * dp; e += 32) {
+            const int r = e / dp, c = e - r * dp;
+            Rs[e] = (r < rows && c < d) ? x[(r0 + r) * d + c] - __ldg(mu + c) : 0.0;
+        }
+        __syncwarp();
+        double a[KTM];
+#pragma unroll
+        for (int ks = 0; ks < KTM; ++ks) a[ks] = ks < KT ? Rs[grp * dp + ks * 4 + tig] : 0.0;
+        double q = 0.0;
+        for (int nt = 0; nt < NT; ++nt) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KTM; ++ks)
+                if (ks < KT) dmma_m8n8k4(c0, c1, a[ks], Ps[(ks * NT + nt) * 32 + lane]);
+            // accumulator layout: row = grp, cols = nt*8 + tig*2 + {0,1}
+            const int col = nt * 8 + tig * 2;
+            q = fma(c0, Rs[grp * dp + col], q);
+            q = fma(c1, Rs[grp * dp + col + 1], q);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        if (tig == 0 && grp < rows) out[r0 + grp] = -0.5 * q + log_norm;
+        __syncwarp();
+    }
+}
+
+int dense_gaussian_eval_launch(const gl_model *m, const double *x, long long n, double *out, cudaStream_t st) {
+    const int d = m->dev.d;
+    const int KT = (d + 3) / 4, NT = (d + 7) / 8;
+    const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;
+    const int smem = (int)(sizeof(double) * ((size_t)KT * NT * 32 + (size_t)DG_WARPS * 8 * dp));
+    long long blocks = ((n + 7) / 8 + DG_WARPS - 1) / DG_WARPS;
+    const long long cap = (long long)sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+#define GL_DG_LAUNCH(KTM)                                                                                        \
+    do {                                                                                                         \
+        if (smem > 48 * 1024)                                                                                    \
+            GL_CUDA(cudaFuncSetAttribute(dense_gaussian_dmma_kernel<KTM>,                                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+        dense_gaussian_dmma_kernel<KTM><<<(int)blocks, DG_WARPS * 32, smem, st>>>(                               \
+            x, n, d, KT, NT, m->dev.aux0, m->dev.aux2, m->dev.s0, out);                                          \
+    } while (0)
+    if (KT <= 4) GL_DG_LAUNCH(4);
+    else if (KT <= 8) GL_DG_LAUNCH(8);
+    else if (KT <= 16) GL_DG_LAUNCH(16);
+    else GL_DG_LAUNCH(32);
+#undef GL_DG_LAUNCH
+    GL_CHECK_LAUNCH();
+    return GL_OK;
+}
+
+int dense_gaussian_pack(const double *P_dev, int d, double *Pf_dev) {
+    const int KT = (d + 3) / 4, NT = (d + 7) / 8;
+    dense_gaussian_pack_kernel<<<(KT * NT * 32 + 255) / 256, 256>>>(P_dev, d, KT, NT, Pf_dev);
+    GL_CHECK_LAUNCH();
+    GL_CUDA(cudaDeviceSynchronize());
+    return GL_OK;
+}
+
+// FP64 tensor-core peak: 4 independent accumulator pairs per warp, back-to-back DMMAs
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double a, double b) {
+    double c[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    for (int i = 0; i < iters; ++i) {
+        dmma_m8n8k4(c[0], c[1], a, b);
+        dmma_m8n8k4(c[2], c[3], a, b);
+        dmma_m8n8k4(c[4], c[5], a, b);
+        dmma_m8n8k4(c[6], c[7], a, b);
+    }
+    const double s = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace gl
+
+extern "C" {
+
+// FP64 tensor-core (DMMA m8n8k4) peak microbenchmark; flops = blocks*8 warps*iters*4*512.
+int gl_microbench_dmma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream) {
+    GL_REQUIRE(blocks >= 1 && iters >= 1 && scratch_dev != nullptr, "bad argument");
+    gl::dmma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch_dev, iters, 1.0000001, 0.9999999);
+    GL_CHECK_LAUNCH();
+    if (flops_out) *flops_out = (int64_t)blocks * 8 * (int64_t)iters * 4 * 512;
+    return GL_OK;
+}
+
+}  // extern "C"

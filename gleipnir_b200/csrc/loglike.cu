@@ -6,6 +6,9 @@
 
 namespace gl {
 
+int dense_gaussian_eval_launch(const gl_model *m, const double *x, long long n, double *out, cudaStream_t st);
+int dense_gaussian_pack(const double *P_dev, int d, double *Pf_dev);
+
 struct EvalLauncher {
     const gl_model *m;
     const double *x;
@@ -26,6 +29,8 @@ int loglike_eval_launch(const gl_model *m, const double *x_dev, long long n, dou
         GL_REQUIRE(m->dev.ext_eval != nullptr, "external model without an eval entry point");
         return m->dev.ext_eval(&m->dev, x_dev, n, logl_dev, (void *)st);
     }
+    if (m->dev.kind == GL_MODEL_DENSE_GAUSSIAN && m->dev.aux2 != nullptr && !m->no_tensor)
+        return dense_gaussian_eval_launch(m, x_dev, n, logl_dev, st);     // FP64 tensor cores (DMMA)
     EvalLauncher L{m, x_dev, n, logl_dev, st};
     return dispatch_model(m->dev.kind, L);
 }
@@ -85,7 +90,9 @@ int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const doubl
     int rc = gl::new_model(GL_MODEL_DENSE_GAUSSIAN, d, out);
     if (rc) return rc;
     gl_model *m = *out;
-    const size_t nd = (size_t)d, bytes = sizeof(double) * (nd + nd * nd);
+    const size_t nd_ = (size_t)d;
+    const size_t KT = (nd_ + 3) / 4, NT = (nd_ + 7) / 8;
+    const size_t nd = (size_t)d, bytes = sizeof(double) * (nd + nd * nd + KT * NT * 32);
     cudaError_t e = cudaMalloc(&m->aux_alloc, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(m->aux_alloc, mu_host, sizeof(double) * nd, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
@@ -99,6 +106,20 @@ int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, const doubl
     m->dev.s0 = log_norm;
     m->dev.aux0 = m->aux_alloc;
     m->dev.aux1 = m->aux_alloc + nd;
+    m->dev.aux2 = m->aux_alloc + nd + nd * nd;
+    rc = gl::dense_gaussian_pack(m->dev.aux1, d, m->aux_alloc + nd + nd * nd);
+    if (rc) {
+        cudaFree(m->aux_alloc);
+        delete m;
+        *out = nullptr;
+        return rc;
+    }
+    return GL_OK;
+}
+
+int gl_model_set_tensor_path(gl_model *m, int32_t enable) {
+    GL_REQUIRE(m != nullptr, "model is NULL");
+    m->no_tensor = enable == 0;
     return GL_OK;
 }
 

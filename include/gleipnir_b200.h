@@ -113,6 +113,9 @@ GL_API int gl_model_create_dense_gaussian(int32_t d, const double *mu_host, cons
  * gleipnir/pysb_utilities/nestedsample_it.py:273-339. */
 GL_API int gl_model_create_external(int32_t d, void *walk_fn, void *eval_fn, const void *blob_host,
                                     int64_t blob_bytes, gl_model **out);
+/* Dense Gaussian: the batch evaluation uses the FP64 tensor cores (DMMA mma.sync.m8n8k4.f64)
+ * by default; enable = 0 selects the scalar DFMA kernel (parity tests compare the two). */
+GL_API int gl_model_set_tensor_path(gl_model *m, int32_t enable);
 GL_API int gl_model_dim(const gl_model *m);
 GL_API int gl_model_kind_of(const gl_model *m);
 GL_API int gl_model_destroy(gl_model *m);
@@ -280,6 +283,8 @@ GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, 
  * `iters` x 8 independent DFMAs each; *flops_out = floating-point operations enqueued.
  * `scratch_dev` must hold blocks*256 doubles.  Time it with CUDA events on `stream`. */
 GL_API int gl_microbench_dfma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream);
+/* Same for the FP64 tensor cores: `blocks` CTAs of 8 warps, `iters` x 4 DMMA m8n8k4 per warp. */
+GL_API int gl_microbench_dmma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream);
 
 #ifdef __cplusplus
 }

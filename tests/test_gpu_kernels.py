@@ -160,3 +160,22 @@ def test_select_ties_nan_neginf_negzero(cuda):
     got, _ = _select(cuda, y, 17)
     assert np.array_equal(got, np.arange(17))
     assert _select(cuda, x, 1)[0][0] == np.argmin(x) == 7   # np.argmin: first NaN wins
+
+
+@pytest.mark.parametrize("d,n", [(50, 100003), (7, 1001), (8, 8), (128, 4099), (3, 1)])
+def test_dense_gaussian_dmma_matches_scalar_kernel_and_oracle(cuda, d, n):
+    """FP64 tensor-core (DMMA) batch kernel vs the scalar DFMA kernel vs numpy, ragged sizes."""
+    from gleipnir_b200 import _lib as L
+    from gleipnir_b200 import likelihoods as lk
+    mu, P, ln = olk.make_c3_dense_gaussian(d, seed=d)
+    mu = mu + np.linspace(-0.3, 0.4, d)
+    like = lk.DenseGaussianLogLikelihood(mu, P, ln)
+    x = np.random.default_rng(d + n).uniform(-5, 5, size=(n, d))
+    tensor = like.evaluate(x)
+    L.check(L.load().gl_model_set_tensor_path(like.device_model(), 0))
+    scalar = like.evaluate(x)
+    L.check(L.load().gl_model_set_tensor_path(like.device_model(), 1))
+    want = olk.dense_gaussian(x, mu, P, ln)
+    np.testing.assert_allclose(tensor, want, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(scalar, want, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(tensor, scalar, rtol=RTOL, atol=1e-10)
