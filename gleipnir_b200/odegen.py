@@ -149,12 +149,73 @@ class MassActionNetwork(object):
         lines.append("};")
         return "\n".join(lines)
 
+    COOP_MIN_SPECIES = 5           # NS <= 4: one system per thread; above: one system per 16/32 lanes
+
+    @property
+    def cooperative(self):
+        return self.ns >= self.COOP_MIN_SPECIES
+
+    def cuda_tables(self):
+        """Table form of the network for the cooperative solver (csrc/ode_coop.cuh)."""
+        ns = self.ns
+        if ns > 32:
+            raise ValueError("networks with more than 32 species are not supported yet")
+        for k, reac, prod, sf in self.reactions:
+            if not 1 <= len(reac) <= 2:
+                raise ValueError("the cooperative solver handles uni- and bimolecular mass-action reactions")
+        gl = 16 if ns <= 16 else 32
+        rx_a = [self._sp(r[1][0]) for r in self.reactions]
+        rx_b = [self._sp(r[1][1]) if len(r[1]) > 1 else -1 for r in self.reactions]
+        rx_k = [self._pp(r[0]) for r in self.reactions]
+        rx_sf = [r[3] for r in self.reactions]
+        row_ptr, row_rx, row_coef = [0], [], []
+        for s_ in self.species:
+            for i, (k, reac, prod, sf) in enumerate(self.reactions):
+                net = prod.count(s_) - reac.count(s_)
+                if net:
+                    row_rx.append(i)
+                    row_coef.append(net)
+            row_ptr.append(len(row_rx))
+        init_kind, init_val, init_par = [], [], []
+        for s_ in self.species:
+            v = self.initials.get(s_, 0.0)
+            init_kind.append(1 if isinstance(v, str) else 0)
+            init_par.append(self._pp(v) if isinstance(v, str) else 0)
+            init_val.append(0.0 if isinstance(v, str) else float(v))
+        obs_ptr, obs_sp, obs_coef = [0], [], []
+        for name in self.obs_names:
+            for s_, c in self.observables[name].items():
+                obs_sp.append(self._sp(s_))
+                obs_coef.append(float(c))
+            obs_ptr.append(len(obs_sp))
+
+        def arr(ctype, name, vals):
+            body = ", ".join(repr(v) if ctype == "double" else str(v) for v in vals) or "0"
+            return "__device__ const %s T_%s[] = {%s};" % (ctype, name, body)
+
+        tables = [arr("int", "rx_a", rx_a), arr("int", "rx_b", rx_b), arr("int", "rx_k", rx_k),
+                  arr("double", "rx_sf", rx_sf), arr("int", "row_ptr", row_ptr), arr("int", "row_rx", row_rx),
+                  arr("int", "row_coef", row_coef), arr("int", "init_kind", init_kind),
+                  arr("double", "init_val", init_val), arr("int", "init_par", init_par),
+                  arr("int", "obs_ptr", obs_ptr), arr("int", "obs_sp", obs_sp), arr("double", "obs_coef", obs_coef)]
+        acc = []
+        for t, name in (("int", "rx_a"), ("int", "rx_b"), ("int", "rx_k"), ("double", "rx_sf"), ("int", "row_ptr"),
+                        ("int", "row_rx"), ("int", "row_coef"), ("int", "init_kind"), ("double", "init_val"),
+                        ("int", "init_par"), ("int", "obs_ptr"), ("int", "obs_sp"), ("double", "obs_coef")):
+            acc.append("    static __device__ __forceinline__ %s %s(int i) { return T_%s[i]; }" % (t, name, name))
+        struct = ["struct Net {",
+                  "    static constexpr int NS = %d, NP = %d, NR = %d, NOBS = %d, GL = %d;"
+                  % (ns, self.np_, len(self.reactions), len(self.obs_names), gl)] + acc + ["};"]
+        return "\n".join(tables + struct)
+
     def plugin_source(self):
+        if self.cooperative:
+            return COOP_PLUGIN_TEMPLATE % dict(name=self.name, struct=self.cuda_tables())
         return PLUGIN_TEMPLATE % dict(name=self.name, struct=self.cuda_struct())
 
     def source_hash(self):
         h = hashlib.sha256(self.plugin_source().encode())
-        for fn in ("ode_like.cuh", "walker.cuh", "loglike.cuh", "likelihoods.cuh", "engine.cuh", "common.cuh",
+        for fn in ("ode_like.cuh", "ode_coop.cuh", "walker.cuh", "loglike.cuh", "likelihoods.cuh", "engine.cuh", "common.cuh",
                    "priors.cuh", "philox.cuh", "select.cuh"):
             with open(os.path.join(CSRC, fn), "rb") as f:
                 h.update(f.read())
@@ -178,6 +239,28 @@ GL_API int gl_plugin_walk_launch(const void *P, const void *M, void *stream) {
 }
 GL_API int gl_plugin_eval_launch(const void *M, const double *x, long long n, double *out, void *stream) {
     return gl::loglike_rows_launch<Like>(*(const gl::ModelDev *)M, x, n, out, (cudaStream_t)stream, 64);
+}
+GL_API const char *gl_plugin_last_error(void) { return gl::error_buffer(); }
+GL_API void gl_plugin_info(int *ns, int *np, int *nobs) {
+    *ns = Net::NS; *np = Net::NP; *nobs = Net::NOBS;
+}
+}
+'''
+
+
+COOP_PLUGIN_TEMPLATE = r'''// GENERATED by gleipnir_b200/odegen.py for network "%(name)s" (cooperative solver) -- do not edit.
+#include "ode_coop.cuh"
+
+namespace {
+%(struct)s
+}  // namespace
+
+extern "C" {
+GL_API int gl_plugin_walk_launch(const void *P, const void *M, void *stream) {
+    return gl::walk_coop_launch<Net>(*(const gl::WalkParams *)P, *(const gl::ModelDev *)M, (cudaStream_t)stream);
+}
+GL_API int gl_plugin_eval_launch(const void *M, const double *x, long long n, double *out, void *stream) {
+    return gl::ode_coop_eval_launch<Net>(*(const gl::ModelDev *)M, x, n, out, (cudaStream_t)stream);
 }
 GL_API const char *gl_plugin_last_error(void) { return gl::error_buffer(); }
 GL_API void gl_plugin_info(int *ns, int *np, int *nobs) {
