@@ -179,3 +179,19 @@ def test_dense_gaussian_dmma_matches_scalar_kernel_and_oracle(cuda, d, n):
     np.testing.assert_allclose(tensor, want, rtol=RTOL, atol=1e-10)
     np.testing.assert_allclose(scalar, want, rtol=RTOL, atol=1e-10)
     np.testing.assert_allclose(tensor, scalar, rtol=RTOL, atol=1e-10)
+
+
+def test_eggcarton_near_cosine_zeros_and_large_arguments(cuda):
+    """The walker's own cos (immediate-coefficient polynomials after Cody-Waite reduction) must stay
+    within 1e-12 of numpy also where cos ~ 0 (odd multiples of pi/2) and far outside the prior box."""
+    from gleipnir_b200 import likelihoods as lk
+    like = lk.EggCartonLogLikelihood(2)
+    base = (np.arange(-40, 41) + 0.5) * np.pi
+    x0 = np.concatenate([base, base + 1e-9, base - 3e-7, np.linspace(-1e4, 1e4, 1001), [1e9, -3e10, 0.0, -0.0]])
+    x = np.stack([x0, np.full_like(x0, 0.3)], axis=1)
+    got = like.evaluate(x)
+    want = olk.eggcarton(x)
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    # d = 1 exposes cos itself: (2 + cos x)^5
+    one = lk.EggCartonLogLikelihood(1)
+    np.testing.assert_allclose(one.evaluate(x0[:, None]), (2.0 + np.cos(x0)) ** 5, rtol=RTOL)
