@@ -318,7 +318,8 @@ __device__ unsigned long long cta_select_kworst(const unsigned long long *keys, 
 }
 
 __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
-    EngineState *S, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
+    EngineState *S, int end_walk_tc /* >= 0: first finish the previous refill (end_walk_kernel's job) */,
+    long long evals_per_walker, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
     long long capacity, const double *__restrict__ live, const double *__restrict__ logl,
     long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, double *__restrict__ dead_x,
     double *__restrict__ dead_logl, double *__restrict__ dead_w, long long *__restrict__ dead_idx,
@@ -327,6 +328,23 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
     __shared__ unsigned int hist[SEL_BINS];
     __shared__ double scratch[33];
     const int tid = threadIdx.x;
+
+    // ---- epilogue of the previous refill, folded in (saves a launch per step) -----------------
+    if (end_walk_tc >= 0) {
+        const int kp = S->k_cur;
+        for (int i = tid; i < kp; i += KILL_SMALL_THREADS) is_dead[dead_list[i]] = 0;
+        const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
+        __syncthreads();
+        if (tid < d) {
+            S->widths[tid] = wnew;
+            for (int c = 0; c < end_walk_tc; ++c) S->acc[c][tid] = 0u;
+        }
+        if (tid == 0) {
+            S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
+            S->step += 1;
+        }
+        __syncthreads();
+    }
 
     // ---- begin: batch size -------------------------------------------------------------------
     long long kk = n_target - S->n_dead;
@@ -816,6 +834,8 @@ struct gl_ns {
     // optional CUDA-event timing of the walker / select launches (bench roofline)
     bool prof;
     bool force_multipass;                         // tests: exercise the multi-launch select path
+    bool end_walk_deferred;                       // last refill's epilogue is still to run
+    bool defer_ok;                                // inside gl_ns_advance: the next op is a kill
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -911,6 +931,16 @@ static void prof_mark(gl_ns *ns, std::vector<cudaEvent_t> &v, cudaStream_t st) {
     v.push_back(e);
 }
 
+static int end_walk_launch(gl_ns *ns, cudaStream_t st, long long evals_per_walker);
+
+// a refill whose epilogue was left for the next fused kill: run it now (anything else is next)
+static int flush_end_walk(gl_ns *ns, cudaStream_t st) {
+    if (!ns->end_walk_deferred) return GL_OK;
+    ns->end_walk_deferred = false;
+    ns->h_step -= 1;                       // end_walk_launch counts the step again
+    return end_walk_launch(ns, st, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d);
+}
+
 static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
     const long long N = ns->cfg.population_size;
     const double n_global = (double)ns->cfg.global_population;
@@ -919,8 +949,11 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
         int rc0 = ensure_smem((const void *)kill_small_kernel, smem);
         if (rc0) return rc0;
         prof_mark(ns, ns->ev_sel, st);
+        const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
+        ns->end_walk_deferred = false;
         kill_small_kernel<<<1, KILL_SMALL_THREADS, smem, st>>>(
-            ns->S, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
+            ns->S, tc_arg, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d, k_req,
+            n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
             ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl,
             ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
         GL_CHECK_LAUNCH();
@@ -928,6 +961,8 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
         ns->prof_sel_launches += 1;
         ns->h_launches += 1;
     } else {
+        int rcf = flush_end_walk(ns, st);
+        if (rcf) return rcf;
         begin_kernel<<<1, 1, 0, st>>>(ns->S, k_req, n_target, N);
         prof_mark(ns, ns->ev_sel, st);
         int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
@@ -970,6 +1005,12 @@ static int refill_launch(gl_ns *ns, cudaStream_t st) {
     prof_mark(ns, ns->ev_walk, st);
     ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
     ns->h_launches += ns->cfg.tuning_cycles + 1;
+    if (ns->defer_ok && ns->cfg.population_size <= KILL_SMALL_MAX_N && !ns->force_multipass) {
+        ns->end_walk_deferred = true;      // the next kill_small_kernel finishes this refill
+        ns->h_step += 1;
+        ns->pending_refill = false;
+        return GL_OK;
+    }
     return end_walk_launch(ns, st, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d);
 }
 
@@ -1025,6 +1066,8 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->initialized = ns->pending_refill = ns->finalized = false;
     ns->prof = false;
     ns->force_multipass = false;
+    ns->end_walk_deferred = false;
+    ns->defer_ok = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
@@ -1125,20 +1168,18 @@ int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream) {
         return GL_ESTATE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (ns->pending_refill && ns->h_n_dead < n_deaths_total) {
-        int rc = gl::refill_launch(ns, st);
-        if (rc) return rc;
-    }
-    while (ns->h_n_dead < n_deaths_total) {
-        int rc = gl::kill_launch(ns, ns->cfg.batch_k, n_deaths_total, st);
-        if (rc) return rc;
+    ns->defer_ok = true;                   // every refill below is followed by a kill
+    int rc = GL_OK;
+    if (ns->pending_refill && ns->h_n_dead < n_deaths_total) rc = gl::refill_launch(ns, st);
+    while (rc == GL_OK && ns->h_n_dead < n_deaths_total) {
+        rc = gl::kill_launch(ns, ns->cfg.batch_k, n_deaths_total, st);
+        if (rc) break;
         if (ns->h_k_last <= 0) break;
-        if (ns->h_n_dead < n_deaths_total) {
-            rc = gl::refill_launch(ns, st);
-            if (rc) return rc;
-        }
+        if (ns->h_n_dead < n_deaths_total) rc = gl::refill_launch(ns, st);
     }
-    return GL_OK;
+    ns->defer_ok = false;
+    if (rc == GL_OK) rc = gl::flush_end_walk(ns, st);
+    return rc;
 }
 
 int gl_ns_finalize(gl_ns *ns, void *stream) {
