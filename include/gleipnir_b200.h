@@ -277,6 +277,20 @@ GL_API int gl_ns_profile_read(gl_ns *ns, double *walk_ms, int64_t *walk_launches
 GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
                    int64_t n_deaths_total, double *dead_host, gl_ns_state *state_out);
 
+/* ---- reference-exact validation mode ----------------------------------------------------------
+ * The reference AS SHIPPED (nested_sampling.py:83-213 + samplers.py:56-152 with its quirks,
+ * numpy's legacy MT19937 stream seeded by `seed`, the reference's draw order), replayed on the
+ * device for scipy `uniform` priors, the 'uniform' proposal and the iid-Gaussian likelihood
+ * -0.5*sum(x*x) + cst -- the configurations whose arithmetic is IEEE-exact on both sides.
+ * weights_host = [w_1..w_n, alpha**n] computed by the caller with the reference's expressions.
+ * dead_host[(n_iterations + N - 1), d + 2] is bit-identical to the reference's `dead_points`;
+ * scalars_host = {Z, H, n_evals, information} (device exp/log: <= 1e-15 relative). */
+GL_API int gl_reference_exact_run_host(uint32_t seed, int32_t N, int32_t d, const double *loc_host,
+                                       const double *scale_host, double cst, int32_t iterations,
+                                       int32_t burn_in, int32_t tuning_cycles, int32_t n_iterations,
+                                       const double *weights_host, double *dead_host, double *widths_host,
+                                       double *scalars_host);
+
 /* ---- measurement helpers ------------------------------------------------------ */
 /* FP64 DFMA-pipe peak microbenchmark (roofline denominator for the walker / ODE kernels;
  * MEASURED_PEAKS.json has no FP64 entry).  Enqueues `blocks` CTAs of 256 threads running

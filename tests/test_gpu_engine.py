@@ -282,3 +282,27 @@ def test_fused_and_multipass_kill_agree_at_the_size_limit(cuda):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
     assert out[0][4] < out[1][4]          # the fused path really launched fewer kernels
+
+
+@pytest.mark.parametrize("name,seed,d,N,skw,n_iter", [
+    ("anchor_gauss5_N20", 0, 5, 20, dict(iterations=10, tuning_cycles=1), 120),
+    ("gauss2_N50_tc0", 3, 2, 50, dict(iterations=5, tuning_cycles=0), 200),
+])
+def test_reference_exact_mode_reproduces_the_real_reference_bit_for_bit(cuda, golden_dir, name, seed, d, N, skw, n_iter):
+    """The reference AS SHIPPED (MT19937 stream, quirks and all) replayed on the GPU: the dead-point
+    table of the real reference run (tests/golden/ref_runs.npz, SURVEY 6.2 anchor) is reproduced
+    bit for bit; evidence/information to 1e-13."""
+    from gleipnir_b200.reference_exact import run_reference_exact
+    g = np.load(os.path.join(golden_dir, "ref_runs.npz"))
+    const = d * (-0.5 * np.log(2 * np.pi))
+    out = run_reference_exact(seed, [-5.0] * d, [10.0] * d, const, N, n_iterations=n_iter, **skw)
+    ref = g[name + "/dead"]
+    assert out["dead"].shape == ref.shape
+    assert np.array_equal(out["dead"], ref)                                   # log_l, weight, x: every bit
+    assert np.array_equal(out["widths"], g[name + "/widths"])
+    np.testing.assert_allclose(out["log_evidence"], g[name + "/logZ"], rtol=1e-13)
+    np.testing.assert_allclose(out["log_evidence_error"], g[name + "/logZ_err"], rtol=1e-12)
+    np.testing.assert_allclose(out["information"], g[name + "/information"], rtol=1e-12)
+    if name == "anchor_gauss5_N20":
+        assert out["n_evals"] == 17989
+        assert abs(out["log_evidence"] - (-9.852104048247114)) < 1e-12
