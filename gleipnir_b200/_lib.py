@@ -101,6 +101,9 @@ _SIGNATURES = {
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
+    "gl_sampler_call_host": (c_int, [POINTER(gl_prior), c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_uint64, c_int32,
+                                     POINTER(c_double), c_double, POINTER(c_double), c_int32, POINTER(c_double),
+                                     POINTER(c_double)]),
     "gl_reference_exact_run_host": (c_int, [c_uint32, c_int32, c_int32, POINTER(c_double), POINTER(c_double), c_double,
                                             c_int32, c_int32, c_int32, c_int32, POINTER(c_double), POINTER(c_double),
                                             POINTER(c_double), POINTER(c_double)]),

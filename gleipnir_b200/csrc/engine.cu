@@ -1367,6 +1367,90 @@ int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t
     return GL_OK;
 }
 
+// ---- the reference's per-call sampler protocol (samplers.py:56): one walker -------------------------
+namespace gl {
+__global__ void single_walker_setup_kernel(EngineState *S, long long *dead_list, unsigned char *is_dead, double lstar,
+                                           int step, const double *widths_in, int d) {
+    S->k_cur = 1;
+    S->do_walk = 1;
+    S->lstar = lstar;
+    S->step = step;
+    dead_list[0] = 0;                 // slot 0 is the one to refill, slot 1 (the start point) the only survivor
+    is_dead[0] = 1;
+    is_dead[1] = 0;
+    if (widths_in)
+        for (int j = 0; j < d; ++j) S->widths[j] = widths_in[j];
+}
+}  // namespace gl
+
+int gl_sampler_call_host(const gl_prior *priors_host, int32_t d, const gl_model *model, int32_t iterations,
+                         int32_t burn_in, int32_t tuning_cycles, int32_t proposal, uint64_t seed, int32_t call_index,
+                         const double *start_host, double ns_boundary, double *widths_inout_host, int32_t have_widths,
+                         double *point_out_host, double *logl_out_host) {
+    GL_REQUIRE(priors_host && model && start_host && widths_inout_host && point_out_host && logl_out_host,
+               "NULL argument");
+    gl_ns_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.population_size = 2;
+    cfg.batch_k = 1;
+    cfg.iterations = iterations;
+    cfg.burn_in = burn_in;
+    cfg.tuning_cycles = tuning_cycles;
+    cfg.proposal = proposal;
+    cfg.seed = seed;
+    cfg.dead_capacity = 4;
+    cfg.global_population = 2;
+    const int64_t ws = gl_ns_workspace_bytes(&cfg, d);
+    if (ws < 0) return (int)ws;
+    const size_t D = (size_t)d;
+    const size_t n_dbl = 2 * D + 2 + 4 * D + 4 + 4 + D;      // live, logl, dead_x, dead_logl, dead_w, widths
+    char *slab = nullptr;
+    GL_CUDA(cudaMalloc(&slab, sizeof(double) * n_dbl + 4 * 8 + 4 * 4 + 256 + (size_t)ws));
+    double *p = (double *)slab;
+    gl_ns_buffers b;
+    b.live = p; p += 2 * D;
+    b.logl = p; p += 2;
+    b.dead_x = p; p += 4 * D;
+    b.dead_logl = p; p += 4;
+    b.dead_w = p; p += 4;
+    double *widths_dev = p; p += D;
+    b.dead_idx = (int64_t *)p; p += 4;
+    b.dead_step = (int32_t *)p; p += 2;
+    b.workspace = (void *)(((uintptr_t)p + 255) / 256 * 256);
+    gl_ns *ns = nullptr;
+    int rc = gl_ns_create(&cfg, priors_host, d, model, &b, &ns);
+    cudaError_t e = cudaSuccess;
+    if (rc == GL_OK) {
+        e = cudaMemcpy(b.live, start_host, sizeof(double) * D, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(b.live + D, start_host, sizeof(double) * D, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && have_widths)
+            e = cudaMemcpy(widths_dev, widths_inout_host, sizeof(double) * D, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = gl::cuda_fail(e, "sampler call upload", __FILE__, __LINE__);
+    }
+    if (rc == GL_OK) rc = gl::loglike_eval_launch(model, b.live, 2, b.logl, 0);          // samplers.py:83
+    if (rc == GL_OK) rc = gl_ns_init(ns, 1, 0);            // state + widths from 100 prior draws (:70-81)
+    if (rc == GL_OK) {
+        gl::single_walker_setup_kernel<<<1, 1>>>(ns->S, ns->dead_list, ns->is_dead, ns_boundary, call_index,
+                                                 have_widths ? widths_dev : nullptr, d);
+        ns->pending_refill = true;
+        ns->h_k_last = 1;
+        rc = gl_ns_refill(ns, 0);
+    }
+    if (rc == GL_OK) {
+        gl_ns_state st;
+        rc = gl_ns_read_state(ns, &st, 0);
+        if (rc == GL_OK) {
+            memcpy(widths_inout_host, st.widths, sizeof(double) * D);
+            e = cudaMemcpy(point_out_host, b.live, sizeof(double) * D, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(logl_out_host, b.logl, sizeof(double), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = gl::cuda_fail(e, "sampler call download", __FILE__, __LINE__);
+        }
+    }
+    if (ns) gl_ns_destroy(ns);
+    cudaFree(slab);
+    return rc;
+}
+
 int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");
     ns->force_multipass = enable != 0;

@@ -277,6 +277,18 @@ GL_API int gl_ns_profile_read(gl_ns *ns, double *walk_ms, int64_t *walk_launches
 GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
                    int64_t n_deaths_total, double *dead_host, gl_ns_state *state_out);
 
+/* ---- the sampler's per-call protocol -------------------------------------------------------------
+ * MetropolisComponentWiseHardNSRejection.__call__(sampled_parameters, loglikelihood, start_param_vec,
+ * ns_boundary) -> (point, logL)  (samplers.py:56-152): ONE walker from `start_host` under the wall
+ * `ns_boundary`, run by the same walker kernel as the batched engine.  `widths_inout_host[d]` carries
+ * the sampler's persistent `_widths` (have_widths = 0 on the first call: initialised from 100 prior
+ * draws as samplers.py:70-81); `call_index` separates the Philox streams of successive calls. */
+GL_API int gl_sampler_call_host(const gl_prior *priors_host, int32_t d, const gl_model *model, int32_t iterations,
+                                int32_t burn_in, int32_t tuning_cycles, int32_t proposal, uint64_t seed,
+                                int32_t call_index, const double *start_host, double ns_boundary,
+                                double *widths_inout_host, int32_t have_widths, double *point_out_host,
+                                double *logl_out_host);
+
 /* ---- reference-exact validation mode ----------------------------------------------------------
  * The reference AS SHIPPED (nested_sampling.py:83-213 + samplers.py:56-152 with its quirks,
  * numpy's legacy MT19937 stream seeded by `seed`, the reference's draw order), replayed on the

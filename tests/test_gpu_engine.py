@@ -306,3 +306,33 @@ def test_reference_exact_mode_reproduces_the_real_reference_bit_for_bit(cuda, go
     if name == "anchor_gauss5_N20":
         assert out["n_evals"] == 17989
         assert abs(out["log_evidence"] - (-9.852104048247114)) < 1e-12
+
+
+def test_sampler_per_call_protocol(cuda):
+    """The reference's sampler protocol (samplers.py:56; tests/test_samplers.py:10-26):
+    sampler(sampled_parameters, loglikelihood, start_param_vec, ns_boundary) -> (point, logL)."""
+    from scipy.stats import norm, uniform
+    from gleipnir.likelihoods import IIDGaussianLogLikelihood
+    from gleipnir.nestedsampling.samplers import MetropolisComponentWiseHardNSRejection
+    from gleipnir.sampled_parameter import SampledParameter
+    s = MetropolisComponentWiseHardNSRejection(iterations=10, tuning_cycles=2)
+    assert (s.iterations, s.burn_in, s.tuning_cycles, s.proposal) == (10, 0, 2, 'uniform')
+    sps = [SampledParameter('a', uniform(-5, 10)), SampledParameter('b', norm(0., 2.))]
+    like = IIDGaussianLogLikelihood(2)
+    start = np.array([0.5, -0.25])
+    boundary = like(start) - 1.0
+    new_point, log_l = s(sps, like, start, boundary, seed=5)
+    assert new_point.shape == (2,) and log_l > boundary
+    assert log_l == like(new_point)                       # returned logL belongs to the returned point (no Q1)
+    assert not np.array_equal(new_point, start)
+    w1 = np.array(s._widths)
+    assert s._first is False and w1.shape == (2,) and np.all(w1 > 0)
+    p2, l2 = s(sps, like, new_point, boundary)            # widths persist across calls (samplers.py:124)
+    assert l2 > boundary and l2 == like(p2)
+    # a wall nothing can pass: the walker stays at the start point (test_samplers.py:21-26 analogue)
+    s2 = MetropolisComponentWiseHardNSRejection(iterations=10, tuning_cycles=2)
+    stuck, l_stuck = s2(sps, like, start, 1e9, seed=1)
+    assert np.array_equal(stuck, start) and l_stuck == like(start)
+    # a bare Python callable cannot run on the device: no CPU fallback
+    with pytest.raises(TypeError):
+        s2(sps, lambda p: 1.0, start, 2.0)
