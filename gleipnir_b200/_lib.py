@@ -101,6 +101,10 @@ _SIGNATURES = {
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
+    "gl_posterior_stats_bytes": (c_int64, []),
+    "gl_posterior_weights": (c_int, [_P, _P, _P, c_int64, c_int32, c_double, _P, _P, POINTER(c_int64), _P]),
+    "gl_posterior_partial_doubles": (c_int64, [c_int64, c_int32, c_int32]),
+    "gl_posterior_histograms": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
     "gl_sampler_call_host": (c_int, [POINTER(gl_prior), c_int32, _P, c_int32, c_int32, c_int32, c_int32, c_uint64, c_int32,
                                      POINTER(c_double), c_double, POINTER(c_double), c_int32, POINTER(c_double),
                                      POINTER(c_double)]),

@@ -269,17 +269,16 @@ class NestedSampling(NestedSamplingBase):
 
     def posteriors(self, nbins=None):
         """{name: (marginal, bin_edges, bin_centers)}: weighted histograms of the dead points
-        (Rice-rule bin count); cached after the first call, as upstream."""
+        (Rice-rule bin count), computed on the device (csrc/posteriors.cu: numpy's own bin
+        assignment rule, deterministic sums); cached after the first call, as upstream."""
         if not self._post_eval:
-            _, nw = self._normalised_weights()
-            mask = nw > 0.0
-            if nbins is None:
-                nbins = 2 * int(np.cbrt(int(mask.sum())))
+            from ..posteriors import device_posteriors
+            vals = self._dead_points.to_numpy(dtype=np.float64)
+            marg, edges, centers = device_posteriors(vals[:, 0], vals[:, 1], vals[:, 2:], self._log_evidence, nbins,
+                                                     device=self.device)
             self._posteriors = dict()
-            for name in self._dead_points.columns[2:]:
-                marginal, edges = np.histogram(self._dead_points[name].to_numpy()[mask], weights=nw[mask],
-                                               density=True, bins=nbins)
-                self._posteriors[name] = (marginal, edges, (edges[:-1] + edges[1:]) / 2.0)
+            for j, name in enumerate(self._dead_points.columns[2:]):
+                self._posteriors[name] = (marg[j], edges[j], centers[j])
             self._post_eval = True
         return self._posteriors
 

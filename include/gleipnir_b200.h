@@ -277,6 +277,21 @@ GL_API int gl_ns_profile_read(gl_ns *ns, double *walk_ms, int64_t *walk_launches
 GL_API int gl_ns_run_host(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d, const gl_model *model,
                    int64_t n_deaths_total, double *dead_host, gl_ns_state *state_out);
 
+/* ---- posteriors(): weighted marginal histograms (nested_sampling.py:266-293) ---------------------
+ * Stage 1 writes the normalised weights w_i*exp(L_i)/Z (as exp(log w + L - ln Z)) and returns the
+ * number of rows with positive weight, from which the caller takes the Rice bin count
+ * nbins = 2*int(cbrt(count)) (:286).  Stage 2 builds, per parameter, np.histogram(x[mask],
+ * weights=.., density=True, bins=nbins) with numpy's own bin-assignment rule, deterministically.
+ * The dead_* pointers are the engine's caller-owned buffers; rows = gl_ns_state.n_rows. */
+GL_API int64_t gl_posterior_stats_bytes(void);
+GL_API int gl_posterior_weights(const double *dead_logl_dev, const double *dead_w_dev, const double *dead_x_dev,
+                                int64_t rows, int32_t d, double log_z, double *nw_dev, void *stats_dev,
+                                int64_t *n_masked_host, void *stream);
+GL_API int64_t gl_posterior_partial_doubles(int64_t rows, int32_t d, int32_t nbins);
+GL_API int gl_posterior_histograms(const double *dead_x_dev, const double *nw_dev, int64_t rows, int32_t d,
+                                   int32_t nbins, const void *stats_dev, double *partial_dev, double *marginal_dev,
+                                   double *edges_dev, double *centers_dev, void *stream);
+
 /* ---- the sampler's per-call protocol -------------------------------------------------------------
  * MetropolisComponentWiseHardNSRejection.__call__(sampled_parameters, loglikelihood, start_param_vec,
  * ns_boundary) -> (point, logL)  (samplers.py:56-152): ONE walker from `start_host` under the wall

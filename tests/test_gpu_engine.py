@@ -336,3 +336,47 @@ def test_sampler_per_call_protocol(cuda):
     # a bare Python callable cannot run on the device: no CPU fallback
     with pytest.raises(TypeError):
         s2(sps, lambda p: 1.0, start, 2.0)
+
+
+@pytest.mark.parametrize("nbins", [None, 7, 64])
+def test_device_posteriors_match_reference_formula(cuda, golden_dir, nbins):
+    """posteriors() on the device vs the reference's own formula (np.histogram with weights,
+    density=True, Rice bins; nested_sampling.py:266-293 as restated bit-exactly in
+    oracle/reference_port.posteriors) on (a) the REAL reference's dead table and (b) a device run."""
+    from gleipnir_b200.posteriors import device_posteriors
+    from oracle.reference_port import posteriors as ref_posteriors
+    g = np.load(os.path.join(golden_dir, "ref_runs.npz"))
+    dead = g["egg_N40_rpm/dead"]
+    Z = float(g["egg_N40_rpm/evidence"])
+    want = ref_posteriors(dead, Z, nbins)
+    marg, edges, centers = device_posteriors(dead[:, 0], dead[:, 1], dead[:, 2:], np.log(Z), nbins)
+    for j, (m, e, c) in enumerate(want):
+        assert marg[j].shape == m.shape
+        np.testing.assert_allclose(edges[j], e, rtol=1e-15, atol=0)
+        np.testing.assert_allclose(marg[j], m, rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(centers[j], c, rtol=1e-15)
+    if nbins is None:      # the recorded first marginal of the reference's own posteriors() call
+        np.testing.assert_allclose(marg[0], g["egg_N40_rpm/post_marginal0"], rtol=1e-11)
+        np.testing.assert_allclose(edges[0], g["egg_N40_rpm/post_edges0"], rtol=1e-15)
+    # (b) a larger table from the device engine, through the NestedSampling API
+    from scipy.stats import uniform
+    from gleipnir_b200.likelihoods import IIDGaussianLogLikelihood
+    from gleipnir_b200.nestedsampling import NestedSampling
+    from gleipnir_b200.nestedsampling.stopping_criterion import NumberOfIterations
+    from gleipnir_b200.sampled_parameter import SampledParameter
+    sps = [SampledParameter(n, uniform(-5, 10)) for n in ("a", "b", "c")]
+    ns = NestedSampling(sps, IIDGaussianLogLikelihood(3), 2000, stopping_criterion=NumberOfIterations(20000), seed=2)
+    ns.run()
+    post = ns.posteriors(nbins)
+    tab = ns.dead_points.to_numpy(dtype=float)
+    want = ref_posteriors(tab, ns.evidence, nbins)
+    for j, name in enumerate(("a", "b", "c")):
+        np.testing.assert_allclose(post[name][0], want[j][0], rtol=1e-10)
+        np.testing.assert_allclose(post[name][1], want[j][1], rtol=1e-15)
+    mean_a = np.sum(post["a"][0] * post["a"][2] * np.diff(post["a"][1]))
+    assert abs(mean_a) < 0.1                                   # posterior of a unit Gaussian is centred
+    moments = ns.posterior_moments(n_resample=20000)
+    if nbins != 7:                                             # 7 bins are too coarse for a variance check
+        assert abs(moments["b"][1] - 1.0) < 0.25               # ~unit variance
+    bp, err = ns.best_fit_posterior()
+    assert bp.shape == (3,) and np.all(err > 0)
