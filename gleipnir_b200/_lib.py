@@ -89,6 +89,7 @@ _SIGNATURES = {
     "gl_ns_read_state": (c_int, [_P, POINTER(gl_ns_state), _P]),
     "gl_ns_shard_candidates": (c_int, [_P, c_int32, _P, _P]),
     "gl_ns_shard_commit": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
+    "gl_ns_shard_commit_scratch": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P]),
     "gl_ns_shard_final_partial": (c_int, [_P, _P, _P]),
     "gl_ns_shard_finalize": (c_int, [_P, _P, c_int32, c_int32, _P]),
     "gl_comm_unique_id_bytes": (c_int, []),

@@ -16,6 +16,7 @@ struct gl_comm {
     int world, rank;
     double *send;        // [cap]        this rank's candidates / partials
     double *recv;        // [world*cap]  gathered
+    double *keys;        // [world*cap]  ordering-key scratch of the fused commit kernel
     size_t cap;
 };
 
@@ -75,9 +76,11 @@ int comm_reserve(gl_comm *c, size_t count) {
     if (count <= c->cap) return GL_OK;
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
-    c->send = c->recv = nullptr;
+    if (c->keys) cudaFree(c->keys);
+    c->send = c->recv = c->keys = nullptr;
     GL_CUDA(cudaMalloc(&c->send, sizeof(double) * count));
     GL_CUDA(cudaMalloc(&c->recv, sizeof(double) * count * (size_t)c->world));
+    GL_CUDA(cudaMalloc(&c->keys, sizeof(double) * count * (size_t)c->world));
     c->cap = count;
     return GL_OK;
 }
@@ -88,6 +91,9 @@ int comm_all_gather(gl_comm *c, const double *send, double *recv, size_t count, 
 }
 
 }  // namespace gl
+
+extern "C" int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
+                                          int32_t k, void *keys_scratch, void *stream);
 
 extern "C" {
 
@@ -113,7 +119,7 @@ int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, gl_comm
     gl_comm *c = new gl_comm();
     c->world = world;
     c->rank = rank;
-    c->send = c->recv = nullptr;
+    c->send = c->recv = c->keys = nullptr;
     c->cap = 0;
     ncclResult_t r = gl::nccl().CommInitRank(&c->comm, world, id, rank);
     if (r != ncclSuccess) {
@@ -128,6 +134,7 @@ int gl_comm_destroy(gl_comm *c) {
     if (!c) return GL_OK;
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
+    if (c->keys) cudaFree(c->keys);
     if (c->comm) gl::nccl().CommDestroy(c->comm);
     delete c;
     return GL_OK;
@@ -160,7 +167,7 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
         if (rc) return rc;
         rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)k, st);
         if (rc) return rc;
-        rc = gl_ns_shard_commit(ns, c->recv, c->world, c->rank, k, stream);
+        rc = gl_ns_shard_commit_scratch(ns, c->recv, c->world, c->rank, k, c->keys, stream);
         if (rc) return rc;
         done += k;
     }

@@ -185,7 +185,7 @@ __device__ unsigned long long cta_select_kworst(const unsigned long long *keys, 
     constexpr int NW = KILL_SMALL_THREADS / 32;
     // ---- radix select on 4-bit digits, NO atomics ------------------------------------------------
     // (1) min/max key -> the leading nibbles they share are skipped; (2) per pass each thread counts
-    // its candidates' digits in two 64-bit words of 8-bit counters (<= 24 keys per thread), widened
+    // its candidates' digits in two 64-bit words of 8-bit counters (<= 255 keys per thread), widened
     // to 16-bit lanes and summed with warp REDUX, one thread per digit sums the 32 warps, and every
     // thread scans the 16 totals redundantly (prefix / k_rem stay in registers: two barriers per
     // pass); (3) the loop stops as soon as the boundary bucket is needed in full (always true once
@@ -447,8 +447,10 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
     double n_global, long long capacity, const long long *__restrict__ cand_list, long long *__restrict__ positions,
     const double *__restrict__ live, const double *__restrict__ logl, long long *__restrict__ dead_list,
     unsigned char *__restrict__ is_dead, double *__restrict__ dead_x, double *__restrict__ dead_logl,
-    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
-    extern __shared__ unsigned long long keys[];
+    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step,
+    unsigned long long *keys_global /* scratch for world*k keys when they do not fit in shared memory */) {
+    extern __shared__ unsigned long long keys_smem[];
+    unsigned long long *keys = keys_global ? keys_global : keys_smem;
     __shared__ unsigned int hist[SEL_BINS];
     __shared__ double scratch[33];
     __shared__ int s_start, s_end;
@@ -1294,21 +1296,35 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
     return GL_OK;
 }
 
+int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                               void *keys_scratch, void *stream);
+
 int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
                        void *stream) {
+    return gl_ns_shard_commit_scratch(ns, gathered_logl_dev, world, rank, k, nullptr, stream);
+}
+
+int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                               void *keys_scratch, void *stream) {
     GL_REQUIRE(ns != nullptr && gathered_logl_dev != nullptr, "NULL argument");
     GL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad world/rank");
     GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k, "k=%d outside [1, batch_k]", k);
     cudaStream_t st = (cudaStream_t)stream;
     const double n_global = (double)ns->cfg.global_population;
-    if ((long long)world * k <= gl::KILL_SMALL_MAX_N && !ns->force_multipass) {
-        const int smem = 8 * world * k;
+    // 8-bit per-thread digit counters bound the single-CTA selection to 24 keys/thread in shared
+    // memory; with the keys in an L2-resident global scratch the same kernel serves world*k up to
+    // 255 keys/thread.
+    const bool fits_smem = (long long)world * k <= gl::KILL_SMALL_MAX_N;
+    const bool fits_global = keys_scratch != nullptr && (long long)world * k <= 255LL * gl::KILL_SMALL_THREADS;
+    if ((fits_smem || fits_global) && !ns->force_multipass) {
+        const int smem = fits_smem ? 8 * world * k : 0;
         int rc0 = gl::ensure_smem((const void *)gl::shard_commit_small_kernel, smem);
         if (rc0) return rc0;
         gl::shard_commit_small_kernel<<<1, gl::KILL_SMALL_THREADS, smem, st>>>(
             ns->S, gathered_logl_dev, world, rank, k, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
             ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
-            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step,
+            fits_smem ? nullptr : (unsigned long long *)keys_scratch);
         GL_CHECK_LAUNCH();
         ns->h_launches += 1;
         ns->h_n_dead += k;

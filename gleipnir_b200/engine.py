@@ -105,6 +105,13 @@ class DeviceEngine(object):
 
     def commit(self, gathered, world, rank, k):
         self._gathered = gathered                       # must outlive the enqueued kernels
+        if int(world) * int(k) > 24576:                 # keys of the fused commit go to a global scratch
+            torch = _torch()
+            if getattr(self, "_key_scratch", None) is None or self._key_scratch.numel() < int(world) * int(k):
+                self._key_scratch = torch.empty(int(world) * int(k), dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.gl_ns_shard_commit_scratch(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
+                                                           self._key_scratch.data_ptr(), self._stream()))
+            return
         _lib.check(self.lib.gl_ns_shard_commit(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
                                                self._stream()))
 

@@ -237,6 +237,10 @@ GL_API int gl_ns_read_state(gl_ns *ns, gl_ns_state *out_host, void *stream);
 GL_API int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *stream);
 GL_API int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
                               void *stream);
+/* same, with a caller-provided scratch of world*k 8-byte words for gathered sets too large for
+ * shared memory (keeps the commit a single fused launch up to world*k = 261 120) */
+GL_API int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
+                                      int32_t k, void *keys_scratch, void *stream);
 GL_API int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *stream);
 GL_API int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank,
                                 void *stream);

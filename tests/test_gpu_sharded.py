@@ -88,3 +88,21 @@ def test_sharded_logz_is_unbiased(cuda):
         run_sharded(dev, LocalComm(world), deaths, k)
         zs.append(dev[0].state().log_z)
     assert abs(np.mean(zs) - (-4.60517)) < 3 * 0.03 / np.sqrt(8) + 0.01, zs
+
+
+def test_large_gathered_set_uses_global_key_scratch(cuda):
+    """world*k = 28 000 > 24 576: the fused commit keeps its keys in a global scratch; results must
+    equal the oracle shards exactly as in the shared-memory case."""
+    from gleipnir_b200 import likelihoods as lk
+    n, k, deaths, world = 32000, 7000, 14000, 4
+    table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * 2
+    dev, ora = _run(world, n, k, deaths, table, lk.IIDGaussianLogLikelihood(2), Model("iid_gaussian", 2),
+                    dict(iterations=2, tuning_cycles=0))
+    for e, o in zip(dev, ora):
+        tab, idx, step = e.dead_table()
+        want = o.result
+        nd = len(want["dead_index"])
+        od = np.lexsort((idx[:nd], step[:nd]))
+        oo = np.lexsort((want["dead_index"], want["dead_batch"]))
+        assert np.array_equal(idx[:nd][od], want["dead_index"][oo])
+        np.testing.assert_allclose(e.state().log_z, want["logZ"], rtol=1e-12)
