@@ -222,10 +222,10 @@ def run_b200_arm(args):
                    seed=seed, walker_lanes=args.walker_lanes)
         if world > 1:                      # one shard per rank; L* by all-gather (NCCL)
             off, n_loc = shard_bounds(N, world, rank)
-            eng = DeviceEngine(table, like.device_model(), n_loc, k, n_deaths, row_offset=off, global_population=N,
+            eng = DeviceEngine(table, like, n_loc, k, n_deaths, row_offset=off, global_population=N,
                                **skw)
         else:
-            eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, **skw)
+            eng = DeviceEngine(table, like, N, k, n_deaths, **skw)
         if profile:
             eng.profile_enable(True)
         flush.zero_()                      # evict L2 between timed iterations

@@ -363,8 +363,13 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
 
     // ---- record (nested_sampling.py:130-133,170-173) --------------------------------------------
     const long long base_row = S->n_rows;
-    const double logw = S->logX - log(n_global + 1.0);
-    const double w = exp(logw);
+    __shared__ double s_logw, s_w;                  // scalar math once, not in all 1024 threads
+    if (tid == 0) {
+        s_logw = S->logX - log(n_global + 1.0);
+        s_w = exp(s_logw);
+    }
+    __syncthreads();
+    const double logw = s_logw, w = s_w;
     const bool room = base_row + k <= capacity;
     if (room) {
         const int step = S->step;

@@ -17,13 +17,19 @@ def _torch():
 
 
 class DeviceEngine(object):
-    """One device-resident NS run: live set, dead-point log, accumulators, widths."""
+    """One device-resident NS run: live set, dead-point log, accumulators, widths.
+
+    ``model_handle`` is a DeviceLogLikelihood (preferred: the engine then keeps it alive) or a raw
+    ``gl_model`` handle, which must outlive the engine."""
 
     def __init__(self, prior_table, model_handle, population_size, batch_k, n_deaths_capacity, iterations=100,
                  burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None, walker_lanes=0, row_offset=0,
                  global_population=None):
         torch = _torch()
         self.lib = _lib.load()
+        if hasattr(model_handle, "device_model"):       # a DeviceLogLikelihood: keep it alive with the engine
+            self._like = model_handle
+            model_handle = model_handle.device_model()
         self.d = len(prior_table)
         self.N = int(population_size)
         self.device = torch.device("cuda" if device is None else device)

@@ -113,7 +113,7 @@ class NestedSampling(NestedSamplingBase):
         off, n_loc = shard_bounds(n, comm.world, rank)
         if k >= n_loc:
             raise ValueError("batch_k (%d) must be smaller than the per-rank population (%d)" % (k, n_loc))
-        eng = DeviceEngine(table, loglike.device_model(), n_loc, k, n_deaths, seed=int(seed_t.item()),
+        eng = DeviceEngine(table, loglike, n_loc, k, n_deaths, seed=int(seed_t.item()),
                            device=self.device, row_offset=off, global_population=n, **scfg)
         self._engine = eng
         run_sharded_native(eng, comm, n_deaths, k)
@@ -155,7 +155,7 @@ class NestedSampling(NestedSamplingBase):
             return self._publish(st, table_rows, n_evals, live, n)
         if verbose:
             print("Generating the initial set of live points with population size {}...".format(n))
-        eng = DeviceEngine(table, loglike.device_model(), n, k, capacity, seed=seed, device=self.device, **scfg)
+        eng = DeviceEngine(table, loglike, n, k, capacity, seed=seed, device=self.device, **scfg)
         self._engine = eng
         if verbose:
             print("Evaluating the loglikelihood function for each live point...")

@@ -19,7 +19,7 @@ RTOL = 1e-12
 
 def _engine(table, dev_like, N, k, cap, multipass=False, **kw):
     from gleipnir_b200.engine import DeviceEngine
-    eng = DeviceEngine(table, dev_like.device_model(), N, k, cap, **kw)
+    eng = DeviceEngine(table, dev_like, N, k, cap, **kw)
     if multipass:        # general multi-launch selection instead of the fused single-CTA kill
         eng.force_multipass_select(True)
     return eng
@@ -380,3 +380,46 @@ def test_device_posteriors_match_reference_formula(cuda, golden_dir, nbins):
         assert abs(moments["b"][1] - 1.0) < 0.25               # ~unit variance
     bp, err = ns.best_fit_posterior()
     assert bp.shape == (3,) and np.all(err > 0)
+
+
+def test_edge_sizes_max_dimension_and_minimal_population(cuda):
+    """GL_MAX_DIM = 128 parameters, and the smallest legal population (N=2, k=1), vs the oracle."""
+    from gleipnir_b200 import likelihoods as lk
+    # d = 128 (the ABI's maximum)
+    d, N, k, deaths = 128, 64, 8, 64
+    table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d
+    want = Engine(table, Model("iid_gaussian", d), N, batch_k=k, iterations=2, tuning_cycles=1, seed=8).run(deaths)
+    eng = _engine(table, lk.IIDGaussianLogLikelihood(d), N, k, deaths, seed=8, iterations=2, tuning_cycles=1)
+    eng.init(); eng.advance(deaths); eng.finalize()
+    tab, idx, _ = eng.dead_table()
+    assert np.array_equal(idx[:deaths], want["dead_index"])
+    np.testing.assert_allclose(tab, want["dead"], rtol=RTOL, atol=1e-13)
+    # N = 2, k = 1
+    table = [(pr.GL_PRIOR_NORM, 0.0, 1.0)]
+    want = Engine(table, Model("iid_gaussian", 1), 2, batch_k=1, iterations=3, tuning_cycles=0, seed=2).run(9)
+    eng = _engine(table, lk.IIDGaussianLogLikelihood(1), 2, 1, 9, seed=2, iterations=3, tuning_cycles=0)
+    eng.init(); eng.advance(9); eng.finalize()
+    tab, idx, _ = eng.dead_table()
+    assert tab.shape == (10, 3) and np.array_equal(idx[:9], want["dead_index"])
+    np.testing.assert_allclose(tab, want["dead"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(eng.state().log_z, want["logZ"], rtol=RTOL)
+
+
+def test_argument_validation_errors_are_loud(cuda):
+    from gleipnir_b200 import _lib as L
+    from gleipnir_b200 import likelihoods as lk
+    from gleipnir_b200.engine import DeviceEngine
+    like = lk.IIDGaussianLogLikelihood(2)
+    with pytest.raises(L.GleipnirB200Error):      # batch_k >= N
+        DeviceEngine([(0, -5.0, 10.0)] * 2, like.device_model(), 10, 10, 10)
+    with pytest.raises(L.GleipnirB200Error):      # model dimension != number of priors
+        DeviceEngine([(0, -5.0, 10.0)] * 3, like.device_model(), 10, 2, 10)
+    with pytest.raises(L.GleipnirB200Error):      # unknown prior family code
+        DeviceEngine([(7, -5.0, 10.0)] * 2, like.device_model(), 10, 2, 10)
+    eng = DeviceEngine([(0, -5.0, 10.0)] * 2, like.device_model(), 10, 2, 10)
+    with pytest.raises(L.GleipnirB200Error):      # advance before init
+        eng.advance(4)
+    from scipy.stats import expon
+    from gleipnir_b200.sampled_parameter import SampledParameter
+    with pytest.raises(TypeError):                # prior family without a device kernel
+        SampledParameter("x", expon()).table_row()

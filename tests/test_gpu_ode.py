@@ -94,7 +94,7 @@ def test_nested_sampling_run_on_dimerization_matches_oracle_engine(cuda, g):
     o = Engine(table, Model("callable", 2, fn=lambda y: ode.loglike(desc, [0, 1], y, ts, rows)), N, batch_k=k,
                iterations=3, tuning_cycles=1, seed=11)
     want = o.run(n_deaths)
-    eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, iterations=3, tuning_cycles=1, seed=11)
+    eng = DeviceEngine(table, like, N, k, n_deaths, iterations=3, tuning_cycles=1, seed=11)
     eng.init(); eng.advance(n_deaths); eng.finalize()
     tab, idx, _ = eng.dead_table()
     st = eng.state()

@@ -18,7 +18,7 @@ def _run(world, n, k, deaths, table, dev_like, ora_model, skw, seed=21):
         off, n_loc = shard_bounds(n, world, r)
         dkw = dict(skw)
         dkw["proposal"] = 1 if dkw.get("proposal") == "normal" else 0
-        dev.append(DeviceEngine(table, dev_like.device_model(), n_loc, k, deaths, seed=seed, row_offset=off,
+        dev.append(DeviceEngine(table, dev_like, n_loc, k, deaths, seed=seed, row_offset=off,
                                 global_population=n, **dkw))
         ora.append(OracleShard(table, ora_model, n_loc, batch_k=k, seed=seed, row_offset=off, global_population=n,
                                **skw))
@@ -62,9 +62,9 @@ def test_world_of_one_sharded_equals_plain_engine(cuda):
     n, k, deaths = 300, 30, 900
     table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * 3
     like = lk.IIDGaussianLogLikelihood(3)
-    a = DeviceEngine(table, like.device_model(), n, k, deaths, seed=4, iterations=5, tuning_cycles=1)
+    a = DeviceEngine(table, like, n, k, deaths, seed=4, iterations=5, tuning_cycles=1)
     run_sharded([a], LocalComm(1), deaths, k)
-    b = DeviceEngine(table, like.device_model(), n, k, deaths, seed=4, iterations=5, tuning_cycles=1)
+    b = DeviceEngine(table, like, n, k, deaths, seed=4, iterations=5, tuning_cycles=1)
     b.init(); b.advance(deaths); b.finalize()
     ta, tb = a.dead_table(), b.dead_table()
     assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
@@ -83,7 +83,7 @@ def test_sharded_logz_is_unbiased(cuda):
         dev = []
         for r in range(world):
             off, n_loc = shard_bounds(n, world, r)
-            dev.append(DeviceEngine(table, like.device_model(), n_loc, k, deaths, seed=seed, row_offset=off,
+            dev.append(DeviceEngine(table, like, n_loc, k, deaths, seed=seed, row_offset=off,
                                     global_population=n, iterations=10, tuning_cycles=1))
         run_sharded(dev, LocalComm(world), deaths, k)
         zs.append(dev[0].state().log_z)

@@ -40,7 +40,7 @@ def main():
     for k in [int(v) for v in a.ks.split(",")]:
         zs, errs, ts = [], [], []
         for seed in range(a.seeds):
-            eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, iterations=a.iterations,
+            eng = DeviceEngine(table, like, N, k, n_deaths, iterations=a.iterations,
                                tuning_cycles=a.tuning_cycles, seed=seed)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

@@ -34,7 +34,7 @@ def main():
     N = a.population or N
     k = a.batch_k or N // 10
     n_deaths = k * a.steps
-    eng = DeviceEngine(table, like.device_model(), N, k, n_deaths, seed=1, **skw)
+    eng = DeviceEngine(table, like, N, k, n_deaths, seed=1, **skw)
     eng.init()
     eng.advance(n_deaths)
     eng.finalize()
