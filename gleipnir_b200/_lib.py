@@ -100,6 +100,7 @@ _SIGNATURES = {
     "gl_ns_advance_sharded": (c_int, [_P, _P, c_int64, c_int32, c_int64, _P]),
     "gl_ns_finalize_sharded": (c_int, [_P, _P, _P]),
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
+    "gl_ns_set_select_path": (c_int, [_P, c_int32]),
     "gl_ns_profile_enable": (c_int, [_P, c_int32]),
     "gl_ns_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64), POINTER(c_double), POINTER(c_int64)]),
     "gl_posterior_stats_bytes": (c_int64, []),

@@ -317,15 +317,224 @@ __device__ unsigned long long cta_select_kworst(const unsigned long long *keys, 
     return kstar;
 }
 
+// ---- incrementally sorted live set (optional path 3; NOT the default, see kill_launch) -------------
+// Only the k slots refilled by the last batch change between two kills, so the live set is kept
+// sorted by (key, slot) in two global (L2-resident) buffers: the refilled entries are sorted with a
+// bitonic network in shared memory and merge-pathed into the surviving run; the k worst are then
+// simply the FRONT of the array -- no pass over all N keys, no histogram.  Same (key, slot) order
+// as the radix paths, and the selected slots are re-sorted ascending so everything downstream
+// (record order, accumulation order, walker assignment) is bit-identical to them.
+constexpr int SORTED_MAX_N = 16384;
+
+__device__ __forceinline__ bool pair_less(unsigned long long ka, unsigned int ia, unsigned long long kb,
+                                          unsigned int ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+// Bitonic sort of 1024*E (key, slot) pairs, ascending, with element i = e*1024 + tid held in
+// registers: partners at strides >= 1024 are other registers of the same thread, strides < 32 are
+// exchanged with warp shuffles, and only strides 32..512 go through shared memory (15 barrier
+// stages for 1024 elements instead of 55).  sk/sv: 1024*E entries of shared scratch.
+template <int E>
+__device__ void cta_bitonic_regs(unsigned long long (&k)[E], unsigned int (&v)[E], unsigned long long *sk,
+                                 unsigned int *sv) {
+    const int tid = threadIdx.x;
+    constexpr int T = KILL_SMALL_THREADS;
+#pragma unroll 1
+    for (int size = 2; size <= T * E; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= T) {                               // register <-> register, same thread
+                const int es = stride / T;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & es) == 0 && (e | es) < E) {
+                        const int i = e * T + tid;
+                        const bool up = (i & size) == 0;
+                        const int f = e | es;
+                        if (pair_less(k[f], v[f], k[e], v[e]) == up) {
+                            const unsigned long long tk = k[e]; k[e] = k[f]; k[f] = tk;
+                            const unsigned int tv = v[e]; v[e] = v[f]; v[f] = tv;
+                        }
+                    }
+                }
+            } else if (stride >= 32) {                       // through shared memory
+#pragma unroll
+                for (int e = 0; e < E; ++e) { sk[e * T + tid] = k[e]; sv[e * T + tid] = v[e]; }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = e * T + tid, j = i ^ stride;
+                    const unsigned long long pk = sk[j];
+                    const unsigned int pv = sv[j];
+                    const bool keep_min = ((i & stride) == 0) == ((i & size) == 0);
+                    const bool p_less = pair_less(pk, pv, k[e], v[e]);
+                    if (p_less == keep_min) { k[e] = pk; v[e] = pv; }
+                }
+                __syncthreads();
+            } else {                                         // inside the warp
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = e * T + tid;
+                    const unsigned long long pk = __shfl_xor_sync(0xffffffffu, k[e], stride);
+                    const unsigned int pv = __shfl_xor_sync(0xffffffffu, v[e], stride);
+                    const bool keep_min = ((i & stride) == 0) == ((i & size) == 0);
+                    const bool p_less = pair_less(pk, pv, k[e], v[e]);
+                    if (p_less == keep_min) { k[e] = pk; v[e] = pv; }
+                }
+            }
+        }
+    }
+}
+
+// Load the nB new (key, slot) pairs, sort them, leave them sorted in shared memory Bk/Bi[0..1024*E).
+template <int E>
+__device__ void sorted_load_and_sort(const double *__restrict__ logl, const long long *__restrict__ dead_list,
+                                     bool ready, int nB, unsigned long long *Bk, unsigned int *Bi) {
+    constexpr int T = KILL_SMALL_THREADS;
+    unsigned long long k[E];
+    unsigned int v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * T + threadIdx.x;
+        if (i < nB) {
+            const unsigned int slot = ready ? (unsigned int)dead_list[i] : (unsigned int)i;
+            k[e] = sort_key(logl[slot]);
+            v[e] = slot;
+        } else {
+            k[e] = ~0ull;
+            v[e] = 0xffffffffu;
+        }
+    }
+    cta_bitonic_regs<E>(k, v, Bk, Bi);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) { Bk[e * T + threadIdx.x] = k[e]; Bi[e * T + threadIdx.x] = v[e]; }
+    __syncthreads();
+}
+
+// Returns the largest selected key; writes dead_list (ascending slot) and is_dead.
+// smem_raw: 12 B x (1024*E) for the sorted new entries, then N bytes of dead flags.
+__device__ unsigned long long cta_sorted_select(EngineState *S, const double *__restrict__ logl, int N, int k,
+                                                unsigned long long *sk0, unsigned long long *sk1, unsigned int *si0,
+                                                unsigned int *si1, unsigned char *smem_raw, int n2,
+                                                long long *__restrict__ dead_list,
+                                                unsigned char *__restrict__ is_dead) {
+    constexpr int T = KILL_SMALL_THREADS, NW = T / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool ready = S->sorted_ready != 0;
+    const int cur = S->sort_cur;
+    const int nB = ready ? S->front_dead : N;           // entries whose logL is new
+    const int nA = N - nB;
+    const unsigned long long *Ak = (cur ? sk1 : sk0) + (N - nA);
+    const unsigned int *Ai = (cur ? si1 : si0) + (N - nA);
+    unsigned long long *Ok = cur ? sk0 : sk1;
+    unsigned int *Oi = cur ? si0 : si1;
+    unsigned long long *Bk = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned int *Bi = reinterpret_cast<unsigned int *>(Bk + n2);
+    unsigned char *flags = reinterpret_cast<unsigned char *>(Bi + n2);          // [N]
+    __shared__ int s_cnt[NW];
+    switch (n2 / T) {
+        case 1: sorted_load_and_sort<1>(logl, dead_list, ready, nB, Bk, Bi); break;
+        case 2: sorted_load_and_sort<2>(logl, dead_list, ready, nB, Bk, Bi); break;
+        case 4: sorted_load_and_sort<4>(logl, dead_list, ready, nB, Bk, Bi); break;
+        case 8: sorted_load_and_sort<8>(logl, dead_list, ready, nB, Bk, Bi); break;
+        default: sorted_load_and_sort<16>(logl, dead_list, ready, nB, Bk, Bi); break;
+    }
+    // ---- merge: thread t owns a contiguous chunk of the surviving run A and the new entries that
+    // fall inside it (binary searches only touch shared memory; the A loads are independent) -----
+    if (nA == 0) {
+        for (int i = tid; i < N; i += T) { Ok[i] = Bk[i]; Oi[i] = Bi[i]; }
+    } else {
+        constexpr int PA = SORTED_MAX_N / T;              // 16: max chunk of A per thread
+        const int per = (nA + T - 1) / T;
+        const int a_lo = tid * per < nA ? tid * per : nA, a_hi = a_lo + per < nA ? a_lo + per : nA;
+        unsigned long long ak[PA + 1];
+        unsigned int ai[PA + 1];
+#pragma unroll
+        for (int q = 0; q <= PA; ++q) {
+            const int a = a_lo + q;
+            if (q <= per && a < nA && a <= a_hi) { ak[q] = Ak[a]; ai[q] = Ai[a]; }
+            else { ak[q] = ~0ull; ai[q] = 0xffffffffu; }
+        }
+        if (a_lo < a_hi) {
+            auto lower_bound_B = [&](unsigned long long key, unsigned int idx) {   // # of B entries < (key, idx)
+                int lo = 0, hi = nB;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (pair_less(Bk[mid], Bi[mid], key, idx)) lo = mid + 1;
+                    else hi = mid;
+                }
+                return lo;
+            };
+            int b = tid == 0 ? 0 : lower_bound_B(ak[0], ai[0]);
+            const int n_own = a_hi - a_lo;
+            const int b_hi = a_hi < nA ? lower_bound_B(ak[n_own], ai[n_own]) : nB;
+            int o = a_lo + b, q = 0;
+            while (q < n_own || b < b_hi) {
+                bool takeA;
+                if (b >= b_hi) takeA = true;
+                else if (q >= n_own) takeA = false;
+                else takeA = pair_less(ak[q], ai[q], Bk[b], Bi[b]);
+                if (takeA) {
+                    unsigned long long kk = ak[0];
+                    unsigned int ii = ai[0];
+#pragma unroll
+                    for (int z = 1; z < PA; ++z) if (z == q) { kk = ak[z]; ii = ai[z]; }   // static register select
+                    Ok[o] = kk; Oi[o] = ii; ++q;
+                } else { Ok[o] = Bk[b]; Oi[o] = Bi[b]; ++b; }
+                ++o;
+            }
+        }
+    }
+    for (int i = tid; i < N; i += T) flags[i] = 0;
+    __syncthreads();                                    // Ok/Oi visible block-wide; flags cleared
+    // ---- the k worst are the front of the merged array: flag them, then emit them in slot order --
+    for (int i = tid; i < k; i += T) flags[Oi[i]] = 1;
+    const unsigned long long kstar = Ok[k - 1];
+    __syncthreads();
+    const int C = (N + NW - 1) / NW;
+    const int lo = wid * C, hi = lo + C < N ? lo + C : N;
+    int cnt = 0;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, i < hi && flags[i]));
+    }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    int run = 0;
+    for (int w = 0; w < wid; ++w) run += s_cnt[w];
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        const bool f = i < hi && flags[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) {
+            dead_list[run + __popc(bal & lanemask_lt)] = i;
+            is_dead[i] = 1;
+        }
+        run += __popc(bal);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        S->sorted_ready = 1;
+        S->sort_cur = cur ^ 1;
+        S->front_dead = k;
+    }
+    return kstar;
+}
+
+template <bool SORTED>
 __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
     EngineState *S, int end_walk_tc /* >= 0: first finish the previous refill (end_walk_kernel's job) */,
     long long evals_per_walker, int k_req, long long n_target, int N, int d, long long row_offset, double n_global,
     long long capacity, const double *__restrict__ live, const double *__restrict__ logl,
     long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, double *__restrict__ dead_x,
     double *__restrict__ dead_logl, double *__restrict__ dead_w, long long *__restrict__ dead_idx,
-    int *__restrict__ dead_step) {
-    extern __shared__ unsigned long long keys[];                 // [N]
-    __shared__ unsigned int hist[SEL_BINS];
+    int *__restrict__ dead_step, unsigned long long *sk0, unsigned long long *sk1, unsigned int *si0,
+    unsigned int *si1, int sort_n2 /* entries of bitonic scratch: 1024 * 2^e */) {
+    extern __shared__ unsigned long long keys[];                 // radix: [N] keys; sorted: bitonic scratch
+    __shared__ unsigned int hist[SORTED ? 64 : SEL_BINS];       // (radix scratch; the sorted path needs none)
     __shared__ double scratch[33];
     const int tid = threadIdx.x;
 
@@ -355,10 +564,15 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
     if (tid == 0) { S->k_cur = k; S->do_walk = 0; }
     if (k <= 0) return;
 
-    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
-    __syncthreads();
-
-    const unsigned long long kstar = cta_select_kworst(keys, N, k, hist, dead_list, is_dead);
+    unsigned long long kstar;
+    if (SORTED) {
+        kstar = cta_sorted_select(S, logl, N, k, sk0, sk1, si0, si1, reinterpret_cast<unsigned char *>(keys), sort_n2,
+                                  dead_list, is_dead);
+    } else {
+        for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
+        __syncthreads();
+        kstar = cta_select_kworst(keys, N, k, hist, dead_list, is_dead);
+    }
     __syncthreads();
 
     // ---- record (nested_sampling.py:130-133,170-173) --------------------------------------------
@@ -833,6 +1047,10 @@ struct gl_ns {
     unsigned char *is_dead;
     double *scratch_x, *scratch_l, *tmp_k, *fin_partials;
     long long *cand_list, *positions;             // sharded run scratch ([k] each)
+    unsigned long long *sk0, *sk1;                // sorted live set: keys (two buffers)
+    unsigned int *si0, *si1;                      //                  slots
+    int select_path;                              // 0 auto, 1 multipass, 2 fused radix, 3 fused sorted
+    bool h_sorted_ready;
     gl::SelectState *sel2;                        // selection state for the gathered candidates
     // host mirrors (deterministic arithmetic; no device reads needed to drive the loop)
     long long h_n_dead, h_n_evals, h_launches;
@@ -853,7 +1071,7 @@ static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct WorkspaceLayout {
     size_t off_state, off_sel, off_pt, off_list, off_isdead, off_sx, off_sl, off_tmp, off_fin, off_cand, off_pos,
-        off_sel2, total;
+        off_sel2, off_sk0, off_sk1, off_si0, off_si1, total;
 };
 
 static WorkspaceLayout workspace_layout(const gl_ns_config &c, int d) {
@@ -872,6 +1090,11 @@ static WorkspaceLayout workspace_layout(const gl_ns_config &c, int d) {
     L.off_cand = o;   o += align256(sizeof(long long) * k);
     L.off_pos = o;    o += align256(sizeof(long long) * k);
     L.off_sel2 = o;   o += align256(sizeof(SelectState));
+    const size_t ns_ = (size_t)c.population_size <= (size_t)SORTED_MAX_N ? (size_t)c.population_size : 0;
+    L.off_sk0 = o;    o += align256(sizeof(unsigned long long) * ns_);
+    L.off_sk1 = o;    o += align256(sizeof(unsigned long long) * ns_);
+    L.off_si0 = o;    o += align256(sizeof(unsigned int) * ns_);
+    L.off_si1 = o;    o += align256(sizeof(unsigned int) * ns_);
     L.total = o;
     return L;
 }
@@ -926,7 +1149,7 @@ static int blocks_for(long long items, int threads, int cap_per_sm) {
 // opt a kernel into > 48 KB of dynamic shared memory (idempotent; raises the limit to the device max once)
 static int ensure_smem(const void *fn, int bytes) {
     if (bytes <= 40 * 1024) return GL_OK;
-    GL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     return GL_OK;
 }
 
@@ -951,18 +1174,39 @@ static int flush_end_walk(gl_ns *ns, cudaStream_t st) {
 static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
     const long long N = ns->cfg.population_size;
     const double n_global = (double)ns->cfg.global_population;
-    if (N <= KILL_SMALL_MAX_N && !ns->force_multipass) {
-        const int smem = (int)(sizeof(unsigned long long) * N);
-        int rc0 = ensure_smem((const void *)kill_small_kernel, smem);
-        if (rc0) return rc0;
-        prof_mark(ns, ns->ev_sel, st);
+    const int path = ns->force_multipass ? 1 : ns->select_path;
+    // auto = fused radix: measured 37 us per kill at N = 10^4, k = 10^3 against 52 us for the sorted-merge
+    // variant (a 1024-entry bitonic sort alone is ~43 k warp-instructions on the one SM that runs the kill)
+    const bool use_sorted = path == 3 && N <= SORTED_MAX_N;
+    const bool use_radix = !use_sorted && (path == 0 || path == 2 || path == 3) && N <= KILL_SMALL_MAX_N;
+    if (use_sorted || use_radix) {
         const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
         ns->end_walk_deferred = false;
-        kill_small_kernel<<<1, KILL_SMALL_THREADS, smem, st>>>(
-            ns->S, tc_arg, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d, k_req,
-            n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
-            ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl,
-            ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+        const long long epw = (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
+        prof_mark(ns, ns->ev_sel, st);
+        if (use_sorted) {
+            // bitonic scratch: 12 B per new entry, padded to a power of two (all N on the first call)
+            int nb = ns->h_sorted_ready ? ns->cfg.batch_k : (int)N, n2 = KILL_SMALL_THREADS;
+            while (n2 < nb) n2 <<= 1;
+            const int smem = 12 * n2 + (int)N + 16;
+            int rc0 = ensure_smem((const void *)kill_small_kernel<true>, smem);
+            if (rc0) return rc0;
+            kill_small_kernel<true><<<1, KILL_SMALL_THREADS, smem, st>>>(
+                ns->S, tc_arg, epw, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global,
+                ns->cfg.dead_capacity, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
+                ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step, ns->sk0, ns->sk1,
+                ns->si0, ns->si1, n2);
+            ns->h_sorted_ready = true;
+        } else {
+            const int smem = (int)(sizeof(unsigned long long) * N);
+            int rc0 = ensure_smem((const void *)kill_small_kernel<false>, smem);
+            if (rc0) return rc0;
+            kill_small_kernel<false><<<1, KILL_SMALL_THREADS, smem, st>>>(
+                ns->S, tc_arg, epw, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global,
+                ns->cfg.dead_capacity, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
+                ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step, nullptr, nullptr,
+                nullptr, nullptr, 0);
+        }
         GL_CHECK_LAUNCH();
         prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;
@@ -1012,7 +1256,7 @@ static int refill_launch(gl_ns *ns, cudaStream_t st) {
     prof_mark(ns, ns->ev_walk, st);
     ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
     ns->h_launches += ns->cfg.tuning_cycles + 1;
-    if (ns->defer_ok && ns->cfg.population_size <= KILL_SMALL_MAX_N && !ns->force_multipass) {
+    if (ns->defer_ok && ns->cfg.population_size <= KILL_SMALL_MAX_N && !ns->force_multipass && ns->select_path != 1) {
         ns->end_walk_deferred = true;      // the next kill_small_kernel finishes this refill
         ns->h_step += 1;
         ns->pending_refill = false;
@@ -1068,6 +1312,12 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->cand_list = (long long *)(w + L.off_cand);
     ns->positions = (long long *)(w + L.off_pos);
     ns->sel2 = (gl::SelectState *)(w + L.off_sel2);
+    ns->sk0 = (unsigned long long *)(w + L.off_sk0);
+    ns->sk1 = (unsigned long long *)(w + L.off_sk1);
+    ns->si0 = (unsigned int *)(w + L.off_si0);
+    ns->si1 = (unsigned int *)(w + L.off_si1);
+    ns->select_path = 0;
+    ns->h_sorted_ready = false;
     ns->h_n_dead = ns->h_n_evals = ns->h_launches = 0;
     ns->h_step = ns->h_k_last = 0;
     ns->initialized = ns->pending_refill = ns->finalized = false;
@@ -1126,6 +1376,7 @@ int gl_ns_init(gl_ns *ns, int32_t skip_population, void *stream) {
     GL_CHECK_LAUNCH();
     ns->h_n_dead = 0;
     ns->h_step = ns->h_k_last = 0;
+    ns->h_sorted_ready = false;
     ns->initialized = true;
     ns->pending_refill = ns->finalized = false;
     return GL_OK;
@@ -1475,6 +1726,13 @@ int gl_sampler_call_host(const gl_prior *priors_host, int32_t d, const gl_model 
 int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");
     ns->force_multipass = enable != 0;
+    return GL_OK;
+}
+
+int gl_ns_set_select_path(gl_ns *ns, int32_t path) {
+    GL_REQUIRE(ns != nullptr && path >= 0 && path <= 3, "path must be 0 (auto), 1 (multi-launch), 2 (fused radix), 3 (fused sorted)");
+    GL_REQUIRE(!ns->h_sorted_ready || path == 0 || path == 3, "cannot leave the sorted path once the run has started");
+    ns->select_path = path;
     return GL_OK;
 }
 

@@ -27,6 +27,10 @@ struct EngineState {                 // one instance in device memory per engine
     long long fin_n_local;           // survivors of this engine (rows it appends)
     long long n_rows_dead;           // rows recorded by deaths (before the survivor rows)
     unsigned long long n_evals;      // log-likelihood evaluations performed by this engine
+    // incrementally sorted live set (kill_small_kernel<true>)
+    int sorted_ready;                // the sorted (key, slot) arrays are valid
+    int sort_cur;                    // which of the two buffers is current
+    int front_dead;                  // leading entries of the current buffer that were killed (now stale)
 };
 
 struct WalkParams {                  // by-value kernel parameter

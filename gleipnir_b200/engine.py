@@ -131,6 +131,10 @@ class DeviceEngine(object):
         self._gathered = gathered
         _lib.check(self.lib.gl_ns_shard_finalize(self._h, gathered.data_ptr(), int(world), int(rank), self._stream()))
 
+    def set_select_path(self, path):
+        """0 auto, 1 multi-launch radix, 2 fused radix, 3 fused sorted-merge."""
+        _lib.check(self.lib.gl_ns_set_select_path(self._h, int(path)))
+
     def profile_enable(self, enable=True):
         _lib.check(self.lib.gl_ns_profile_enable(self._h, 1 if enable else 0))
 
