@@ -46,7 +46,8 @@ class gl_ns_state(Structure):
                 ("step", c_int32),
                 ("finalized", c_int32), ("log_x", c_double), ("lstar", c_double), ("z_linear", c_double),
                 ("h_linear", c_double), ("lse_m", c_double), ("lse_z", c_double), ("lse_h", c_double),
-                ("log_z", c_double), ("information", c_double), ("widths", c_double * GL_MAX_DIM)]
+                ("log_z", c_double), ("information", c_double), ("widths", c_double * GL_MAX_DIM),
+                ("shard_overflow", c_int32), ("reserved", c_int32)]
 
 
 _P = c_void_p            # device / opaque pointers
@@ -97,7 +98,10 @@ _SIGNATURES = {
     "gl_comm_create": (c_int, [c_int32, c_int32, _P, POINTER(_P)]),
     "gl_comm_destroy": (c_int, [_P]),
     "gl_comm_all_gather_f64": (c_int, [_P, _P, _P, c_int64, _P]),
-    "gl_ns_advance_sharded": (c_int, [_P, _P, c_int64, c_int32, c_int64, _P]),
+    "gl_ns_advance_sharded": (c_int, [_P, _P, c_int64, c_int32, c_int64, c_double, _P]),
+    "gl_ns_shard_candidate_count": (c_int32, [c_int32, c_int32, c_int64, c_double]),
+    "gl_ns_shard_commit_truncated": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "gl_ns_local_population": (c_int64, [_P]),
     "gl_ns_finalize_sharded": (c_int, [_P, _P, _P]),
     "gl_ns_force_multipass_select": (c_int, [_P, c_int32]),
     "gl_ns_set_select_path": (c_int, [_P, c_int32]),

@@ -92,8 +92,10 @@ int comm_all_gather(gl_comm *c, const double *send, double *recv, size_t count, 
 
 }  // namespace gl
 
-extern "C" int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
-                                          int32_t k, void *keys_scratch, void *stream);
+extern "C" int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
+                                            int32_t k, int32_t m, void *keys_scratch, void *stream);
+extern "C" int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas);
+extern "C" int64_t gl_ns_local_population(const gl_ns *ns);
 
 extern "C" {
 
@@ -148,12 +150,13 @@ int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev,
 // Enqueue the sharded run until `n_deaths_total` GLOBAL deaths: per step candidates -> NCCL
 // all-gather -> commit -> refill, all on `stream`.
 int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
-                          void *stream) {
+                          double candidate_sigmas, void *stream) {
     GL_REQUIRE(ns != nullptr && c != nullptr, "NULL argument");
     GL_REQUIRE(batch_k >= 1, "batch_k must be >= 1");
     int rc = gl::comm_reserve(c, (size_t)(batch_k > 4 ? batch_k : 4));
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_local = gl_ns_local_population(ns);
     int64_t done = n_dead_so_far;
     bool first = true;
     while (done < n_deaths_total) {
@@ -163,11 +166,12 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
             if (rc) return rc;
         }
         first = false;
-        rc = gl_ns_shard_candidates(ns, k, c->send, stream);
+        const int32_t m = gl_ns_shard_candidate_count(k, c->world, n_local, candidate_sigmas);
+        rc = gl_ns_shard_candidates(ns, m, c->send, stream);
         if (rc) return rc;
-        rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)k, st);
+        rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)m, st);
         if (rc) return rc;
-        rc = gl_ns_shard_commit_scratch(ns, c->recv, c->world, c->rank, k, c->keys, stream);
+        rc = gl_ns_shard_commit_truncated(ns, c->recv, c->world, c->rank, k, m, c->keys, stream);
         if (rc) return rc;
         done += k;
     }

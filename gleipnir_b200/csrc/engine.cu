@@ -133,17 +133,33 @@ __global__ void __launch_bounds__(256) shard_gather_kernel(const long long *__re
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) out[i] = logl[cand_list[i]];
 }
 
-// `positions` = the global k worst as ascending positions in the gathered [G*k] array (rank-major,
+// Truncated exchange: every rank contributes only its m <= k worst slots.  The global selection
+// over the [world*m] gathered keys is provably the true k worst iff no rank had ALL m of its
+// candidates selected (a rank whose m-th worst survived cannot hide anything below the threshold).
+// `positions` is ascending, so rank r's share is a contiguous run found by two binary searches.
+__device__ __forceinline__ int lower_bound_pos(const long long *__restrict__ positions, int k, long long v) {
+    int a = 0, b = k;
+    while (a < b) { const int mid = (a + b) >> 1; if (positions[mid] < v) a = mid + 1; else b = mid; }
+    return a;
+}
+__device__ __forceinline__ bool shard_exchange_overflowed(const long long *__restrict__ positions, int k, int m, int r) {
+    const int lo = lower_bound_pos(positions, k, (long long)r * m), hi = lower_bound_pos(positions, k, (long long)(r + 1) * m);
+    return hi - lo >= m;
+}
+
+// `positions` = the global k worst as ascending positions in the gathered [G*m] array (rank-major,
 // slot-ascending inside a rank, i.e. global-index order).  This rank's share is the contiguous run
-// of positions inside [rank*k, (rank+1)*k): translate it back to local slots, flag them dead and
+// of positions inside [rank*m, (rank+1)*m): translate it back to local slots, flag them dead and
 // publish the local batch size.
 __global__ void __launch_bounds__(256) shard_local_kernel(EngineState *S, const long long *__restrict__ positions,
-                                                          const long long *__restrict__ cand_list, int k, int rank,
+                                                          const long long *__restrict__ cand_list, int k, int m,
+                                                          int world, int rank,
                                                           long long *__restrict__ dead_list,
                                                           unsigned char *__restrict__ is_dead) {
     __shared__ int s_start, s_end;
+    if (m < k && threadIdx.x < world && shard_exchange_overflowed(positions, k, m, threadIdx.x)) S->shard_overflow = 1;
     if (threadIdx.x == 0) {
-        const long long lo_pos = (long long)rank * k, hi_pos = lo_pos + k;
+        const long long lo_pos = (long long)rank * m, hi_pos = lo_pos + m;
         int a = 0, b = k;                          // lower_bound(positions, lo_pos)
         while (a < b) { const int m = (a + b) >> 1; if (positions[m] < lo_pos) a = m + 1; else b = m; }
         s_start = a;
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(256) shard_local_kernel(EngineState *S, const 
     __syncthreads();
     const int start = s_start, n_loc = s_end - s_start;
     for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
-        const long long slot = cand_list[positions[start + i] - (long long)rank * k];
+        const long long slot = cand_list[positions[start + i] - (long long)rank * m];
         dead_list[i] = slot;
         is_dead[slot] = 1;
     }
@@ -662,7 +678,7 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_candidates_small_ker
 // share to local slots, dead-row record and the (redundant, identical on every rank) evidence
 // update -- one launch.  Same forms as shard_local_kernel + record_kernel + accumulate_kernel.
 __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
-    EngineState *S, const double *__restrict__ gathered, int world, int rank, int k, int d, long long row_offset,
+    EngineState *S, const double *__restrict__ gathered, int world, int rank, int k, int m, int d, long long row_offset,
     double n_global, long long capacity, const long long *__restrict__ cand_list, long long *__restrict__ positions,
     const double *__restrict__ live, const double *__restrict__ logl, long long *__restrict__ dead_list,
     unsigned char *__restrict__ is_dead, double *__restrict__ dead_x, double *__restrict__ dead_logl,
@@ -674,13 +690,14 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
     __shared__ double scratch[33];
     __shared__ int s_start, s_end;
     const int tid = threadIdx.x;
-    const int n = world * k;
+    const int n = world * m;
     for (int i = tid; i < n; i += KILL_SMALL_THREADS) keys[i] = sort_key(gathered[i]);
     __syncthreads();
     const unsigned long long kstar = cta_select_kworst(keys, n, k, hist, positions, nullptr);
     __syncthreads();
+    if (m < k && tid >= 32 && tid < 32 + world && shard_exchange_overflowed(positions, k, m, tid - 32)) S->shard_overflow = 1;
     if (tid == 0) {
-        const long long lo_pos = (long long)rank * k, hi_pos = lo_pos + k;
+        const long long lo_pos = (long long)rank * m, hi_pos = lo_pos + m;
         int a = 0, b = k;
         while (a < b) { const int m = (a + b) >> 1; if (positions[m] < lo_pos) a = m + 1; else b = m; }
         s_start = a;
@@ -691,7 +708,7 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
     __syncthreads();
     const int start = s_start, n_loc = s_end - s_start;
     for (int i = tid; i < n_loc; i += KILL_SMALL_THREADS) {
-        const long long slot = cand_list[positions[start + i] - (long long)rank * k];
+        const long long slot = cand_list[positions[start + i] - (long long)rank * m];
         dead_list[i] = slot;
         is_dead[slot] = 1;
     }
@@ -1498,6 +1515,8 @@ int gl_ns_read_state(gl_ns *ns, gl_ns_state *out, void *stream) {
     out->n_launches = ns->h_launches;
     out->step = h.step;
     out->finalized = h.finalized;
+    out->shard_overflow = h.shard_overflow;
+    out->reserved = 0;
     out->log_x = h.logX;
     out->lstar = h.lstar;
     out->z_linear = h.Z_lin;
@@ -1552,32 +1571,54 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
     return GL_OK;
 }
 
-int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
-                               void *keys_scratch, void *stream);
+int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                                 int32_t m, void *keys_scratch, void *stream);
 
 int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
                        void *stream) {
-    return gl_ns_shard_commit_scratch(ns, gathered_logl_dev, world, rank, k, nullptr, stream);
+    return gl_ns_shard_commit_truncated(ns, gathered_logl_dev, world, rank, k, k, nullptr, stream);
 }
 
 int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
                                void *keys_scratch, void *stream) {
+    return gl_ns_shard_commit_truncated(ns, gathered_logl_dev, world, rank, k, k, keys_scratch, stream);
+}
+
+int64_t gl_ns_local_population(const gl_ns *ns) { return ns ? ns->cfg.population_size : 0; }
+
+int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas) {
+    if (k < 1 || world < 1 || n_local < 2) return 0;
+    long long m = k;
+    if (world > 1 && sigmas > 0.0) {
+        // deaths per rank ~ Binomial(k, 1/world): mean + `sigmas` standard deviations + a small floor
+        const double p = 1.0 / (double)world;
+        m = (long long)ceil((double)k * p + sigmas * sqrt((double)k * p * (1.0 - p)) + 8.0);
+    }
+    if (m > k) m = k;
+    if (m > n_local - 1) m = n_local - 1;
+    if (m * world < k) m = (k + world - 1) / world;       // the union must hold k keys
+    return (int32_t)m;
+}
+
+int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank, int32_t k,
+                                 int32_t m, void *keys_scratch, void *stream) {
     GL_REQUIRE(ns != nullptr && gathered_logl_dev != nullptr, "NULL argument");
     GL_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad world/rank");
     GL_REQUIRE(k >= 1 && k <= ns->cfg.batch_k, "k=%d outside [1, batch_k]", k);
+    GL_REQUIRE(m >= 1 && m <= k && (long long)m * world >= k, "candidates per rank m=%d outside [ceil(k/world), k]", m);
     cudaStream_t st = (cudaStream_t)stream;
     const double n_global = (double)ns->cfg.global_population;
     // 8-bit per-thread digit counters bound the single-CTA selection to 24 keys/thread in shared
     // memory; with the keys in an L2-resident global scratch the same kernel serves world*k up to
     // 255 keys/thread.
-    const bool fits_smem = (long long)world * k <= gl::KILL_SMALL_MAX_N;
-    const bool fits_global = keys_scratch != nullptr && (long long)world * k <= 255LL * gl::KILL_SMALL_THREADS;
+    const bool fits_smem = (long long)world * m <= gl::KILL_SMALL_MAX_N;
+    const bool fits_global = keys_scratch != nullptr && (long long)world * m <= 255LL * gl::KILL_SMALL_THREADS;
     if ((fits_smem || fits_global) && !ns->force_multipass) {
-        const int smem = fits_smem ? 8 * world * k : 0;
+        const int smem = fits_smem ? 8 * world * m : 0;
         int rc0 = gl::ensure_smem((const void *)gl::shard_commit_small_kernel, smem);
         if (rc0) return rc0;
         gl::shard_commit_small_kernel<<<1, gl::KILL_SMALL_THREADS, smem, st>>>(
-            ns->S, gathered_logl_dev, world, rank, k, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
+            ns->S, gathered_logl_dev, world, rank, k, m, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
             ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
             ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step,
             fits_smem ? nullptr : (unsigned long long *)keys_scratch);
@@ -1588,10 +1629,11 @@ int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32
         ns->pending_refill = true;
         return GL_OK;
     }
-    int rc = gl::select_launch(gathered_logl_dev, (long long)world * k, nullptr, k, 0, ns->positions, nullptr, nullptr,
+    GL_REQUIRE(world <= 256, "world=%d > 256", world);
+    int rc = gl::select_launch(gathered_logl_dev, (long long)world * m, nullptr, k, 0, ns->positions, nullptr, nullptr,
                                ns->sel2, st);
     if (rc) return rc;
-    gl::shard_local_kernel<<<1, 256, 0, st>>>(ns->S, ns->positions, ns->cand_list, k, rank, ns->dead_list,
+    gl::shard_local_kernel<<<1, 256, 0, st>>>(ns->S, ns->positions, ns->cand_list, k, m, world, rank, ns->dead_list,
                                               ns->is_dead);
     gl::record_kernel<<<gl::blocks_for((long long)k * ns->d, 256, 8), 256, 0, st>>>(
         ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),

@@ -31,6 +31,7 @@ struct EngineState {                 // one instance in device memory per engine
     int sorted_ready;                // the sorted (key, slot) arrays are valid
     int sort_cur;                    // which of the two buffers is current
     int front_dead;                  // leading entries of the current buffer that were killed (now stale)
+    int shard_overflow;              // sticky: a truncated candidate exchange could not prove its selection exact
 };
 
 struct WalkParams {                  // by-value kernel parameter

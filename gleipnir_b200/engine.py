@@ -110,16 +110,22 @@ class DeviceEngine(object):
         return out
 
     def commit(self, gathered, world, rank, k):
+        """`gathered` holds m = len/world candidates per rank (m <= k: truncated exchange)."""
         self._gathered = gathered                       # must outlive the enqueued kernels
-        if int(world) * int(k) > 24576:                 # keys of the fused commit go to a global scratch
+        n = int(gathered.numel())
+        m = n // int(world)
+        scratch = None
+        if n > 24576:                                   # keys of the fused commit go to a global scratch
             torch = _torch()
-            if getattr(self, "_key_scratch", None) is None or self._key_scratch.numel() < int(world) * int(k):
-                self._key_scratch = torch.empty(int(world) * int(k), dtype=torch.int64, device=self.device)
-            _lib.check(self.lib.gl_ns_shard_commit_scratch(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
-                                                           self._key_scratch.data_ptr(), self._stream()))
-            return
-        _lib.check(self.lib.gl_ns_shard_commit(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
-                                               self._stream()))
+            if getattr(self, "_key_scratch", None) is None or self._key_scratch.numel() < n:
+                self._key_scratch = torch.empty(n, dtype=torch.int64, device=self.device)
+            scratch = self._key_scratch.data_ptr()
+        _lib.check(self.lib.gl_ns_shard_commit_truncated(self._h, gathered.data_ptr(), int(world), int(rank), int(k),
+                                                         m, scratch, self._stream()))
+
+    def overflowed(self):
+        """True when a truncated candidate exchange could not prove one of its steps exact."""
+        return bool(self.state().shard_overflow)
 
     def final_partial(self):
         torch = _torch()

@@ -8,8 +8,8 @@ code drives one CUDA engine per process over NCCL (production), several CUDA eng
 process (single-GPU emulation for tests), or -- in the CPU test-suite only -- numpy oracle
 shards over gloo:
 
-  shard ops    init() / candidates(k) / commit(gathered, world, rank, k) / refill() /
-               final_partial() / finalize_sharded(gathered, world, rank)
+  shard ops    init() / candidates(m) / commit(gathered, world, rank, k) / refill() /
+               final_partial() / finalize_sharded(gathered, world, rank) / overflowed()
                (``DeviceEngine`` implements them on the GPU)
   comm         world, ranks (global rank of each local shard), all_gather(list of local arrays)
                -> rank-major concatenation over the whole world
@@ -62,15 +62,33 @@ def shard_bounds(n_global, world, rank):
     return rank * n_local, n_local
 
 
-def run_sharded(shards, comm, n_deaths, batch_k, init=True):
-    """Run the local `shards` (engines of the ranks ``comm.ranks``) to ``n_deaths`` global deaths."""
-    if init:
-        for sh in shards:
-            sh.init()
+DEFAULT_CANDIDATE_SIGMAS = 8.0
+
+
+def candidate_count(k, world, n_local, sigmas):
+    """Candidates each rank contributes to a step of k global deaths (same arithmetic as
+    ``gl_ns_shard_candidate_count``): the k deaths fall on a rank as Binomial(k, 1/world), so
+    mean + `sigmas` standard deviations (+8) covers it; the commit proves each step exact and
+    raises the overflow flag when it cannot.  ``sigmas <= 0``: the full k per rank."""
+    import math
+    m = int(k)
+    if world > 1 and sigmas > 0.0:
+        p = 1.0 / float(world)
+        m = int(math.ceil(float(k) * p + sigmas * math.sqrt(float(k) * p * (1.0 - p)) + 8.0))
+    m = min(m, int(k), int(n_local) - 1)
+    if m * world < k:
+        m = (int(k) + world - 1) // world
+    return m
+
+
+def _run_sharded_once(shards, comm, n_deaths, batch_k, sigmas):
+    for sh in shards:
+        sh.init()
     done = 0
     while done < n_deaths:
         k = min(int(batch_k), n_deaths - done)
-        gathered = comm.all_gather([sh.candidates(k) for sh in shards])
+        m = candidate_count(k, comm.world, shards[0].N, sigmas)
+        gathered = comm.all_gather([sh.candidates(m) for sh in shards])
         for sh, r in zip(shards, comm.ranks):
             sh.commit(gathered, comm.world, r, k)
         done += k
@@ -80,6 +98,16 @@ def run_sharded(shards, comm, n_deaths, batch_k, init=True):
     partials = comm.all_gather([sh.final_partial() for sh in shards])
     for sh, r in zip(shards, comm.ranks):
         sh.finalize_sharded(partials, comm.world, r)
+    return done
+
+
+def run_sharded(shards, comm, n_deaths, batch_k, candidate_sigmas=DEFAULT_CANDIDATE_SIGMAS):
+    """Run the local `shards` (engines of the ranks ``comm.ranks``) to ``n_deaths`` global deaths.
+    A truncated candidate exchange that could not prove one of its steps exact (the flag is
+    identical on every rank) is repeated from the start with the full exchange."""
+    done = _run_sharded_once(shards, comm, n_deaths, batch_k, candidate_sigmas)
+    if candidate_sigmas > 0.0 and any(sh.overflowed() for sh in shards):
+        done = _run_sharded_once(shards, comm, n_deaths, batch_k, 0.0)
     return done
 
 
@@ -152,10 +180,22 @@ def gather_dead_tables(engine, group=None):
     return cat[:, :d + 2], cat[:, d + 2].astype(np.int64), cat[:, d + 3].astype(np.int64)
 
 
-def run_sharded_native(engine, nccl_comm, n_deaths, batch_k):
-    """Whole sharded run enqueued from C++ (gl_ns_advance_sharded / gl_ns_finalize_sharded)."""
+def run_sharded_native(engine, nccl_comm, n_deaths, batch_k, candidate_sigmas=DEFAULT_CANDIDATE_SIGMAS,
+                       check_overflow=True):
+    """Whole sharded run enqueued from C++ (gl_ns_advance_sharded / gl_ns_finalize_sharded).
+    ``check_overflow`` reads the state back (one sync) and repeats the run with the full exchange
+    when the truncated one could not prove a step exact; returns True when that happened."""
     from . import _lib
-    engine.init()
     st = engine._stream()
-    _lib.check(engine.lib.gl_ns_advance_sharded(engine._h, nccl_comm.h, int(n_deaths), int(batch_k), 0, st))
-    _lib.check(engine.lib.gl_ns_finalize_sharded(engine._h, nccl_comm.h, st))
+
+    def once(sigmas):
+        engine.init()
+        _lib.check(engine.lib.gl_ns_advance_sharded(engine._h, nccl_comm.h, int(n_deaths), int(batch_k), 0,
+                                                    float(sigmas), st))
+        _lib.check(engine.lib.gl_ns_finalize_sharded(engine._h, nccl_comm.h, st))
+
+    once(candidate_sigmas)
+    if check_overflow and candidate_sigmas > 0.0 and engine.overflowed():
+        once(0.0)
+        return True
+    return False

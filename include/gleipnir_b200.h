@@ -178,6 +178,9 @@ typedef struct gl_ns_state {
     double log_z;         /* ln Z from the scaled accumulators                           */
     double information;   /* -ln Z + H/Z (:125,167,194)                                  */
     double widths[GL_MAX_DIM]; /* current proposal widths (`_widths`, samplers.py:50,124) */
+    int32_t shard_overflow; /* sharded run: a truncated candidate exchange could not prove a step exact
+                             * (the results must be discarded and the run repeated with a full exchange) */
+    int32_t reserved;
 } gl_ns_state;
 
 typedef struct gl_ns gl_ns;
@@ -241,6 +244,19 @@ GL_API int gl_ns_shard_commit(gl_ns *ns, const double *gathered_logl_dev, int32_
  * shared memory (keeps the commit a single fused launch up to world*k = 261 120) */
 GL_API int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
                                       int32_t k, void *keys_scratch, void *stream);
+/* Truncated exchange.  With the live points spread at random over the ranks, a rank holds
+ * Binomial(k, 1/world) of a step's k deaths, so exchanging all k candidates per rank is mostly
+ * wasted work (and the redundant selection over world*k keys is the scaling bottleneck).
+ * gl_ns_shard_candidate_count returns m = mean + `sigmas` standard deviations (clamped to
+ * [ceil(k/world), min(k, n_local-1)]; sigmas <= 0 or world == 1: m = k).  Steps 1-3 then run with
+ * m candidates per rank: gl_ns_shard_candidates(ns, m, ...), all-gather of m doubles,
+ * gl_ns_shard_commit_truncated(..., k, m, ...).  The commit PROVES the selection exact (no rank had
+ * all m of its candidates selected); when it cannot, it raises the sticky gl_ns_state.shard_overflow
+ * flag and the caller repeats the run with m = k -- results are never silently approximate. */
+GL_API int64_t gl_ns_local_population(const gl_ns *ns);
+GL_API int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas);
+GL_API int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int32_t world, int32_t rank,
+                                        int32_t k, int32_t m, void *keys_scratch, void *stream);
 GL_API int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *stream);
 GL_API int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank,
                                 void *stream);
@@ -255,9 +271,11 @@ GL_API int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, 
 GL_API int gl_comm_destroy(gl_comm *c);
 GL_API int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream);
 /* Enqueue steps (refill of the waiting batch, candidates, all-gather, commit) until
- * `n_deaths_total` global deaths; `n_dead_so_far` = global deaths already recorded. */
+ * `n_deaths_total` global deaths; `n_dead_so_far` = global deaths already recorded.
+ * `candidate_sigmas` > 0 selects the truncated exchange (check gl_ns_state.shard_overflow after
+ * the run); 0 exchanges all k candidates per rank. */
 GL_API int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k,
-                                 int64_t n_dead_so_far, void *stream);
+                                 int64_t n_dead_so_far, double candidate_sigmas, void *stream);
 GL_API int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream);
 
 /* Populations whose ordering keys fit in shared memory (N <= 24576) use a single-CTA fused

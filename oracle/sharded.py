@@ -21,9 +21,14 @@ class OracleShard(Engine):
 
     def commit(self, gathered, world, rank, k):
         gathered = np.asarray(gathered, dtype=np.float64)
+        m = len(gathered) // world                          # candidates per rank (m <= k: truncated exchange)
         order = select_k_worst(gathered, k)                 # death order over the whole world
         pos = np.sort(order)
-        mine = pos[(pos >= rank * k) & (pos < (rank + 1) * k)] - rank * k
+        if m < k:                                           # exactness proof: no rank had all m selected
+            per_rank = np.bincount(pos // m, minlength=world)
+            if (per_rank >= m).any():
+                self.shard_overflow = True
+        mine = pos[(pos >= rank * m) & (pos < (rank + 1) * m)] - rank * m
         local = self._cand[mine]
         logw = self.logX - np.log(self.n_global + 1.0)
         w = np.exp(logw)
@@ -36,6 +41,20 @@ class OracleShard(Engine):
         self.n_dead += k
         self.last_dead = local
         self.lstar = gathered[order[-1]]
+
+    def overflowed(self):
+        return bool(getattr(self, "shard_overflow", False))
+
+    def init(self, *a, **kw):
+        # a full restart, like gl_ns_init on the device (a run repeated after an overflow)
+        from .engine import Accumulators
+        self.shard_overflow = False
+        self.acc = Accumulators()
+        self.logX, self.n_dead, self.step, self.n_evals = 0.0, 0, 0, 0
+        self.dead_rows, self.dead_index, self.dead_batch = [], [], []
+        self.last_dead = np.zeros(0, dtype=np.int64)
+        self.lstar = -np.inf
+        return super().init(*a, **kw)
 
     def refill(self, injected=None):
         if len(self.last_dead) == 0:

@@ -11,7 +11,7 @@ from oracle.sharded import OracleShard
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, n, k, deaths, table, dev_like, ora_model, skw, seed=21):
+def _run(world, n, k, deaths, table, dev_like, ora_model, skw, seed=21, sigmas=8.0):
     from gleipnir_b200.engine import DeviceEngine
     dev, ora = [], []
     for r in range(world):
@@ -22,8 +22,8 @@ def _run(world, n, k, deaths, table, dev_like, ora_model, skw, seed=21):
                                 global_population=n, **dkw))
         ora.append(OracleShard(table, ora_model, n_loc, batch_k=k, seed=seed, row_offset=off, global_population=n,
                                **skw))
-    run_sharded(dev, LocalComm(world), deaths, k)
-    run_sharded(ora, LocalComm(world), deaths, k)
+    run_sharded(dev, LocalComm(world), deaths, k, candidate_sigmas=sigmas)
+    run_sharded(ora, LocalComm(world), deaths, k, candidate_sigmas=0.0)      # ground truth: full exchange
     return dev, ora
 
 
@@ -97,7 +97,7 @@ def test_large_gathered_set_uses_global_key_scratch(cuda):
     n, k, deaths, world = 32000, 7000, 14000, 4
     table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * 2
     dev, ora = _run(world, n, k, deaths, table, lk.IIDGaussianLogLikelihood(2), Model("iid_gaussian", 2),
-                    dict(iterations=2, tuning_cycles=0))
+                    dict(iterations=2, tuning_cycles=0), sigmas=0.0)
     for e, o in zip(dev, ora):
         tab, idx, step = e.dead_table()
         want = o.result
@@ -106,3 +106,71 @@ def test_large_gathered_set_uses_global_key_scratch(cuda):
         oo = np.lexsort((want["dead_index"], want["dead_batch"]))
         assert np.array_equal(idx[:nd][od], want["dead_index"][oo])
         np.testing.assert_allclose(e.state().log_z, want["logZ"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("multipass", [False, True])
+def test_truncated_exchange_matches_full_exchange_oracle(cuda, multipass):
+    """m < k candidates per rank (k = 400 over 4 ranks: m = 178): the committed selection is
+    proven exact on the device and equals the oracle's full exchange bit for bit."""
+    from gleipnir_b200 import likelihoods as lk
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.sharded import _run_sharded_once, candidate_count
+    n, k, deaths, world = 4000, 400, 2400, 4
+    assert candidate_count(k, world, n // world, 8.0) == 178
+    table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * 2
+    skw = dict(iterations=4, tuning_cycles=1)
+    dev, ora = [], []
+    for r in range(world):
+        off, n_loc = shard_bounds(n, world, r)
+        e = DeviceEngine(table, lk.EggCartonLogLikelihood(2), n_loc, k, deaths, seed=5, row_offset=off,
+                         global_population=n, **skw)
+        if multipass:
+            e.force_multipass_select(True)
+        dev.append(e)
+        ora.append(OracleShard(table, Model("eggcarton", 2), n_loc, batch_k=k, seed=5, row_offset=off,
+                               global_population=n, **skw))
+    _run_sharded_once(dev, LocalComm(world), deaths, k, 8.0)
+    assert not any(e.overflowed() for e in dev)
+    _run_sharded_once(ora, LocalComm(world), deaths, k, 0.0)
+    for e, o in zip(dev, ora):
+        tab, idx, step = e.dead_table()
+        want = o.result
+        nd = len(want["dead_index"])
+        od = np.lexsort((idx[:nd], step[:nd]))
+        oo = np.lexsort((want["dead_index"], want["dead_batch"]))
+        assert np.array_equal(idx[:nd][od], want["dead_index"][oo])
+        np.testing.assert_allclose(tab[:nd][od], want["dead"][:nd][oo], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(e.state().log_z, want["logZ"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("multipass", [False, True])
+def test_truncated_exchange_overflow_is_detected_and_repeated(cuda, multipass):
+    """A margin of ~0 sigmas cannot cover the binomial spread of deaths over the ranks: the device
+    raises shard_overflow (same verdict on every rank) and run_sharded repeats the run in full."""
+    from gleipnir_b200 import likelihoods as lk
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.sharded import _run_sharded_once
+    n, k, deaths, world = 4000, 1200, 6000, 2
+    table = [(pr.GL_PRIOR_UNIFORM, -5.0, 10.0)] * 2
+    skw = dict(iterations=3, tuning_cycles=0)
+
+    def engines():
+        out = []
+        for r in range(world):
+            off, n_loc = shard_bounds(n, world, r)
+            e = DeviceEngine(table, lk.IIDGaussianLogLikelihood(2), n_loc, k, deaths, seed=9, row_offset=off,
+                             global_population=n, **skw)
+            if multipass:
+                e.force_multipass_select(True)
+            out.append(e)
+        return out
+    probe = engines()
+    _run_sharded_once(probe, LocalComm(world), deaths, k, 1e-9)
+    assert all(e.overflowed() for e in probe)
+    auto, full = engines(), engines()
+    run_sharded(auto, LocalComm(world), deaths, k, candidate_sigmas=1e-9)
+    run_sharded(full, LocalComm(world), deaths, k, candidate_sigmas=0.0)
+    for a, b in zip(auto, full):
+        ta, tb = a.dead_table(), b.dead_table()
+        assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
+        assert a.state().log_z == b.state().log_z and not a.overflowed()
