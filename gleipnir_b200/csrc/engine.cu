@@ -9,6 +9,7 @@
 #include <vector>
 #include "engine.cuh"
 #include "philox.cuh"
+#include <cooperative_groups.h>
 
 namespace gl {
 
@@ -660,6 +661,366 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
     }
 }
 
+// ---- fused kill on a thread-block cluster -------------------------------------------------------
+// The single-CTA kill is bound by the instruction issue rate of the ONE SM it runs on (r01_d
+// profile: 124 k warp-instructions, 32 us).  Here a cluster of KC_CTAS CTAs splits the live set into
+// contiguous chunks (keys in each CTA's shared memory); every radix pass exchanges the 16 digit
+// counts of each CTA through distributed shared memory (one cluster barrier, ~0.2 us), every CTA
+// takes the same decision, the index-ordered compaction gets its global offsets from an exclusive
+// prefix over the CTA totals, the dead-row copy is spread over the cluster, and CTA 0 does the
+// evidence update with the SAME summation tree as the 1024-thread single-CTA kernel (two virtual
+// threads per thread), so every selection path leaves bit-identical state.
+constexpr int KC_CTAS = 8;                      // portable cluster size
+constexpr int KC_THREADS = 512;
+constexpr int KC_NW = KC_THREADS / 32;
+constexpr int KC_MAX_N = KC_CTAS * 24 * 1024;   // 192 KB of keys per CTA; <= 48 keys per thread (8-bit counters)
+
+struct ClusterXchg {                            // per-CTA mailbox, read by the other CTAs via DSMEM
+    unsigned long long kmin, kmax, kstar;
+    unsigned int hist[2][16];
+    unsigned int lt, eq;
+};
+
+// deterministic sums/max over 1024 virtual threads held two per thread (virtual tid, tid + 512):
+// identical tree to block_sum / block_max of a 1024-thread block
+__device__ __forceinline__ double block_sum_v2(double a, double b, double *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = a; scratch[KC_NW + wid] = b; }
+    __syncthreads();
+    if (wid == 0) {
+        double t = warp_sum(scratch[lane]);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+__device__ __forceinline__ double block_max_v2(double a, double b, double *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_max(a);
+    b = warp_max(b);
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = a; scratch[KC_NW + wid] = b; }
+    __syncthreads();
+    if (wid == 0) {
+        double t = warp_max(scratch[lane]);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) kill_cluster_kernel(
+    EngineState *S, int end_walk_tc, long long evals_per_walker, int k_req, long long n_target, int N, int d,
+    long long row_offset, double n_global, long long capacity, const double *__restrict__ live,
+    const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
+    double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
+    long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    extern __shared__ unsigned long long keys[];                 // this CTA's chunk of ordering keys
+    __shared__ ClusterXchg X;
+    __shared__ unsigned int wh[KC_NW * 8];                       // per-warp packed digit counts / lt,eq counts
+    __shared__ unsigned int tot[16];
+    __shared__ unsigned long long mm[2 * KC_NW];
+    __shared__ unsigned long long bc[4];                         // broadcast slots
+    __shared__ double scratch[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // ---- snapshot of the state every CTA needs (CTA 0 rewrites S only at the very end) -----------
+    const int kp = S->k_cur;
+    const int step_now = S->step + (end_walk_tc >= 0 ? 1 : 0);
+    const long long n_dead0 = S->n_dead, base_row = S->n_rows;
+    const double logX0 = S->logX, m_old = S->M;
+
+    // ---- epilogue of the previous refill (end_walk_kernel's job), spread over the cluster ---------
+    if (end_walk_tc >= 0) {
+        for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
+        if (c == 0) {
+            const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
+            __syncthreads();
+            if (tid < d) {
+                S->widths[tid] = wnew;
+                for (int q = 0; q < end_walk_tc; ++q) S->acc[q][tid] = 0u;
+            }
+        }
+    }
+    long long kk = n_target - n_dead0;
+    if (kk > k_req) kk = k_req;
+    if (kk > N - 1) kk = N - 1;
+    if (kk < 0) kk = 0;
+    const int k = (int)kk;
+    if (k <= 0) {
+        if (c == 0 && tid == 0) {
+            if (end_walk_tc >= 0) { S->n_evals += (unsigned long long)((long long)kp * evals_per_walker); S->step = step_now; }
+            S->k_cur = 0;
+            S->do_walk = 0;
+        }
+        return;
+    }
+
+    // ---- load this CTA's chunk --------------------------------------------------------------------
+    const int Nc = (N + KC_CTAS - 1) / KC_CTAS;
+    const int lo_g = c * Nc;
+    const int n_loc = N - lo_g < 0 ? 0 : (N - lo_g < Nc ? N - lo_g : Nc);
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int i = tid; i < n_loc; i += KC_THREADS) {
+        const unsigned long long key = sort_key(logl[lo_g + i]);
+        keys[i] = key;
+        kmin = key < kmin ? key : kmin;
+        kmax = key > kmax ? key : kmax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b2 = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b2 > kmax ? b2 : kmax;
+    }
+    if (lane == 0) { mm[wid] = kmin; mm[KC_NW + wid] = kmax; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 0; w < KC_NW; ++w) {
+            const unsigned long long a = mm[w], b2 = mm[KC_NW + w];
+            kmin = a < kmin ? a : kmin;
+            kmax = b2 > kmax ? b2 : kmax;
+        }
+        X.kmin = kmin;
+        X.kmax = kmax;
+    }
+    cluster.sync();                                              // (also: every is_dead clear above is done)
+    if (wid == 0) {
+        unsigned long long a = ~0ull, b2 = 0ull;
+        if (lane < KC_CTAS) {
+            const ClusterXchg *R = cluster.map_shared_rank(&X, lane);
+            a = R->kmin;
+            b2 = R->kmax;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long a2 = __shfl_xor_sync(0xffffffffu, a, o), b3 = __shfl_xor_sync(0xffffffffu, b2, o);
+            a = a2 < a ? a2 : a;
+            b2 = b3 > b2 ? b3 : b2;
+        }
+        if (lane == 0) { bc[0] = a; bc[1] = b2; }
+    }
+    __syncthreads();
+    kmin = bc[0];
+    kmax = bc[1];
+
+    // ---- radix select, 4-bit digits (same decisions as cta_select_kworst) ---------------------------
+    const unsigned long long diff = kmin ^ kmax;
+    const int first_pass = diff ? __clzll((long long)diff) >> 2 : 16;
+    unsigned long long prefix = first_pass ? kmin >> (64 - 4 * first_pass) : 0ull;
+    int k_rem = k;
+    int sel_shift = 0;
+    if (!diff) prefix = kmin;
+    for (int pass = first_pass; pass < 16; ++pass) {
+        const int shift = 60 - 4 * pass, par = pass & 1;
+        unsigned long long lo8 = 0ull, hi8 = 0ull;
+        for (int i = tid; i < n_loc; i += KC_THREADS) {
+            const unsigned long long key = keys[i];
+            if (pass == 0 || (key >> (shift + 4)) == prefix) {
+                const unsigned int dg = (unsigned int)(key >> shift) & 15u;
+                const unsigned long long inc = 1ull << ((dg & 7u) << 3);
+                if (dg < 8u) lo8 += inc; else hi8 += inc;
+            }
+        }
+        unsigned int pk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pk[q] = (unsigned int)((lo8 >> (16 * q)) & 0xffull) | ((unsigned int)((lo8 >> (16 * q + 8)) & 0xffull) << 16);
+            pk[4 + q] = (unsigned int)((hi8 >> (16 * q)) & 0xffull) | ((unsigned int)((hi8 >> (16 * q + 8)) & 0xffull) << 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pk[q] = __reduce_add_sync(0xffffffffu, pk[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wh[wid * 8 + q] = pk[q];
+        }
+        __syncthreads();
+        if (tid < 16) {
+            unsigned int t = 0u;
+#pragma unroll
+            for (int w = 0; w < KC_NW; ++w) t += (wh[w * 8 + (tid >> 1)] >> ((tid & 1) << 4)) & 0xffffu;
+            X.hist[par][tid] = t;
+        }
+        cluster.sync();
+        if (tid < 16) {
+            unsigned int t = 0u;
+#pragma unroll
+            for (int r = 0; r < KC_CTAS; ++r) t += cluster.map_shared_rank(&X, r)->hist[par][tid];
+            tot[tid] = t;
+        }
+        __syncthreads();
+        int run = 0, digit = 15, run_at = 0, c_at = 0;
+        bool found = false;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int cq = (int)tot[q];
+            if (!found && run + cq >= k_rem) { found = true; digit = q; run_at = run; c_at = cq; }
+            run += cq;
+        }
+        prefix = (prefix << 4) | (unsigned long long)digit;
+        k_rem -= run_at;
+        sel_shift = shift;
+        if (c_at == k_rem) break;
+    }
+    const unsigned long long T = prefix;
+    const int r_ties = k_rem;
+
+    // ---- index-ordered compaction: warp w owns local slots [w*C, (w+1)*C) ---------------------------
+    const int C = (Nc + KC_NW - 1) / KC_NW;
+    const int lo = wid * C, hi = lo + C < n_loc ? lo + C : n_loc;
+    int my_lt = 0, my_eq = 0;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        const unsigned long long kh = i < hi ? keys[i] >> sel_shift : ~0ull;
+        my_lt += __popc(__ballot_sync(0xffffffffu, i < hi && kh < T));
+        my_eq += __popc(__ballot_sync(0xffffffffu, i < hi && kh == T));
+    }
+    __syncthreads();                                             // wh: last pass's readers are done
+    if (lane == 0) { wh[wid] = (unsigned)my_lt; wh[KC_NW + wid] = (unsigned)my_eq; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int a = 0u, b2 = 0u;
+        for (int w = 0; w < KC_NW; ++w) { a += wh[w]; b2 += wh[KC_NW + w]; }
+        X.lt = a;
+        X.eq = b2;
+    }
+    cluster.sync();
+    if (tid == 0) {
+        unsigned int a = 0u, b2 = 0u;
+        for (int r = 0; r < c; ++r) {
+            const ClusterXchg *R = cluster.map_shared_rank(&X, r);
+            a += R->lt;
+            b2 += R->eq;
+        }
+        tot[0] = a;
+        tot[1] = b2;
+    }
+    __syncthreads();
+    int run_lt = (int)tot[0], run_eq = (int)tot[1];
+    for (int w = 0; w < wid; ++w) { run_lt += (int)wh[w]; run_eq += (int)wh[KC_NW + w]; }
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    unsigned long long kstar = 0ull;
+    for (int t0 = lo; t0 < hi; t0 += 32) {
+        const int i = t0 + lane;
+        const unsigned long long key = i < hi ? keys[i] : ~0ull;
+        const unsigned long long kh = i < hi ? key >> sel_shift : ~0ull;
+        const bool is_lt = i < hi && kh < T, is_eq = i < hi && kh == T;
+        const unsigned b_lt = __ballot_sync(0xffffffffu, is_lt), b_eq = __ballot_sync(0xffffffffu, is_eq);
+        const int lt_before = run_lt + __popc(b_lt & lanemask_lt);
+        const int eq_before = run_eq + __popc(b_eq & lanemask_lt);
+        if (is_lt || (is_eq && eq_before < r_ties)) {
+            const int pos = lt_before + (eq_before < r_ties ? eq_before : r_ties);
+            dead_list[pos] = lo_g + i;
+            is_dead[lo_g + i] = 1;
+            kstar = key > kstar ? key : kstar;
+        }
+        run_lt += __popc(b_lt);
+        run_eq += __popc(b_eq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kstar, o);
+        kstar = a > kstar ? a : kstar;
+    }
+    if (lane == 0) mm[wid] = kstar;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 0; w < KC_NW; ++w) { const unsigned long long a = mm[w]; kstar = a > kstar ? a : kstar; }
+        X.kstar = kstar;
+    }
+    cluster.sync();                                              // dead_list complete and visible cluster-wide
+
+    // ---- record: rows spread over the cluster --------------------------------------------------------
+    const double logw = logX0 - log(n_global + 1.0);
+    const double w = exp(logw);
+    const bool room = base_row + k <= capacity;
+    if (room) {
+        for (int e = c * KC_THREADS + tid; e < k * d; e += KC_CTAS * KC_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const long long slot = dead_list[q];
+            dead_x[(base_row + q) * d + j] = live[slot * d + j];
+            if (j == 0) {
+                dead_logl[base_row + q] = logl[slot];
+                dead_w[base_row + q] = w;
+                dead_idx[base_row + q] = slot + row_offset;
+                dead_step[base_row + q] = step_now;
+            }
+        }
+    }
+
+    // ---- accumulate on CTA 0 (virtual 1024-thread tree: same bits as kill_small_kernel) ---------------
+    if (c == 0) {
+        if (wid == 0) {
+            unsigned long long a = lane < KC_CTAS ? cluster.map_shared_rank(&X, lane)->kstar : 0ull;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const unsigned long long a2 = __shfl_xor_sync(0xffffffffu, a, o);
+                a = a2 > a ? a2 : a;
+            }
+            if (lane == 0) bc[2] = a;
+        }
+        double mxa = -INFINITY, mxb = -INFINITY;
+        for (int i = tid; i < k; i += 2 * KC_THREADS) {
+            const double lw = logw + logl[dead_list[i]];
+            if (isfinite(lw)) mxa = fmax(mxa, lw);
+        }
+        for (int i = tid + KC_THREADS; i < k; i += 2 * KC_THREADS) {
+            const double lw = logw + logl[dead_list[i]];
+            if (isfinite(lw)) mxb = fmax(mxb, lw);
+        }
+        const double mx = block_max_v2(mxa, mxb, scratch);
+        const double m_new = fmax(m_old, mx);
+        double sz[2] = {0.0, 0.0}, sh[2] = {0.0, 0.0}, zl[2] = {0.0, 0.0}, hl[2] = {0.0, 0.0};
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            for (int i = tid + v * KC_THREADS; i < k; i += 2 * KC_THREADS) {
+                const double L = logl[dead_list[i]];
+                const double lw = logw + L;
+                if (isfinite(lw)) {
+                    const double t = exp(lw - m_new);
+                    sz[v] += t;
+                    sh[v] += t * L;
+                }
+                const double dZ = w * exp(L);
+                zl[v] += dZ;
+                const double dH = dZ * L;
+                if (dH == dH) hl[v] += dH;
+            }
+        }
+        const double szs = block_sum_v2(sz[0], sz[1], scratch);
+        const double shs = block_sum_v2(sh[0], sh[1], scratch);
+        const double zls = block_sum_v2(zl[0], zl[1], scratch);
+        const double hls = block_sum_v2(hl[0], hl[1], scratch);
+        if (tid == 0) {
+            if (mx > -INFINITY) {
+                const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+                S->Zs = S->Zs * scale + szs;
+                S->Hs = S->Hs * scale + shs;
+                S->M = m_new;
+            }
+            S->Z_lin += zls;
+            S->H_lin += hls;
+            S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
+            S->n_dead = n_dead0 + k;
+            if (room) S->n_rows = base_row + k;
+            S->lstar = key_to_double(bc[2]);
+            S->k_cur = k;
+            S->do_walk = n_dead0 + k < n_target;
+            if (end_walk_tc >= 0) {
+                S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
+                S->step = step_now;
+            }
+        }
+    }
+    cluster.sync();                                              // nobody exits while its mailbox may still be read
+}
+
 // ---- fused single-CTA kernels of the sharded step (local N and world*k both <= KILL_SMALL_MAX_N) --
 // candidates: this rank's k worst slots (ascending slot order) and their logL, one launch
 __global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_candidates_small_kernel(
@@ -1194,9 +1555,11 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
     const int path = ns->force_multipass ? 1 : ns->select_path;
     // auto = fused radix: measured 37 us per kill at N = 10^4, k = 10^3 against 52 us for the sorted-merge
     // variant (a 1024-entry bitonic sort alone is ~43 k warp-instructions on the one SM that runs the kill)
+    // and 36 us -> ?? for the 8-CTA cluster version (path 4), which also serves N up to 196 608 in one launch
     const bool use_sorted = path == 3 && N <= SORTED_MAX_N;
-    const bool use_radix = !use_sorted && (path == 0 || path == 2 || path == 3) && N <= KILL_SMALL_MAX_N;
-    if (use_sorted || use_radix) {
+    const bool use_cluster = !use_sorted && (path == 0 || path == 4) && N <= KC_MAX_N;
+    const bool use_radix = !use_sorted && !use_cluster && (path == 0 || path == 2 || path == 3 || path == 4) && N <= KILL_SMALL_MAX_N;
+    if (use_sorted || use_radix || use_cluster) {
         const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
         ns->end_walk_deferred = false;
         const long long epw = (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
@@ -1214,6 +1577,14 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
                 ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step, ns->sk0, ns->sk1,
                 ns->si0, ns->si1, n2);
             ns->h_sorted_ready = true;
+        } else if (use_cluster) {
+            const int smem = (int)(sizeof(unsigned long long) * ((N + KC_CTAS - 1) / KC_CTAS));
+            int rc0 = ensure_smem((const void *)kill_cluster_kernel, smem);
+            if (rc0) return rc0;
+            kill_cluster_kernel<<<KC_CTAS, KC_THREADS, smem, st>>>(
+                ns->S, tc_arg, epw, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global,
+                ns->cfg.dead_capacity, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
+                ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
         } else {
             const int smem = (int)(sizeof(unsigned long long) * N);
             int rc0 = ensure_smem((const void *)kill_small_kernel<false>, smem);
@@ -1772,7 +2143,8 @@ int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable) {
 }
 
 int gl_ns_set_select_path(gl_ns *ns, int32_t path) {
-    GL_REQUIRE(ns != nullptr && path >= 0 && path <= 3, "path must be 0 (auto), 1 (multi-launch), 2 (fused radix), 3 (fused sorted)");
+    GL_REQUIRE(ns != nullptr && path >= 0 && path <= 4,
+               "path must be 0 (auto), 1 (multi-launch), 2 (fused radix), 3 (fused sorted), 4 (cluster radix)");
     GL_REQUIRE(!ns->h_sorted_ready || path == 0 || path == 3, "cannot leave the sorted path once the run has started");
     ns->select_path = path;
     return GL_OK;

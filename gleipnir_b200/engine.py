@@ -138,7 +138,7 @@ class DeviceEngine(object):
         _lib.check(self.lib.gl_ns_shard_finalize(self._h, gathered.data_ptr(), int(world), int(rank), self._stream()))
 
     def set_select_path(self, path):
-        """0 auto, 1 multi-launch radix, 2 fused radix, 3 fused sorted-merge."""
+        """0 auto, 1 multi-launch radix, 2 fused single-CTA radix, 3 fused sorted-merge, 4 cluster radix."""
         _lib.check(self.lib.gl_ns_set_select_path(self._h, int(path)))
 
     def profile_enable(self, enable=True):

@@ -282,9 +282,10 @@ GL_API int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream);
  * kill kernel; this switch forces the general multi-launch selection path (used by tests so
  * that both paths are checked against each other and the oracle). */
 GL_API int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable);
-/* Selection path: 0 auto (N <= 24576: fused single-CTA radix select; else multi-launch),
- * 1 multi-launch, 2 fused radix, 3 fused kill over an incrementally sorted live set (N <= 16384;
- * measured slower than the radix select on one SM, kept as a tested alternative).
+/* Selection path: 0 auto (N <= 196608: fused kill on an 8-CTA thread-block cluster; else
+ * multi-launch), 1 multi-launch, 2 fused single-CTA radix (N <= 24576), 3 fused kill over an
+ * incrementally sorted live set (N <= 16384; measured slower than the radix select on one SM, kept
+ * as a tested alternative), 4 cluster radix.
  * All paths produce identical results (tests compare them). */
 GL_API int gl_ns_set_select_path(gl_ns *ns, int32_t path);
 

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-PATHS = {"sorted": 3, "radix": 2, "multipass": 1}      # the three selection paths (all must agree)
+PATHS = {"sorted": 3, "radix": 2, "multipass": 1, "cluster": 4}      # the selection paths (all must agree)
 
 
 def _engine(table, dev_like, N, k, cap, multipass=False, **kw):
@@ -28,7 +28,7 @@ def _engine(table, dev_like, N, k, cap, multipass=False, **kw):
     return eng
 
 
-@pytest.mark.parametrize("multipass", ["sorted", "radix", "multipass"])
+@pytest.mark.parametrize("multipass", ["cluster", "sorted", "radix", "multipass"])
 @pytest.mark.parametrize("name", ["plain", "ties", "neginf", "nan", "N1000"])
 def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name, multipass):
     """Identical initial logL + identical replacement stream -> identical dead rows, order and
@@ -64,7 +64,7 @@ def test_outer_loop_replay_matches_real_reference(cuda, golden_dir, name, multip
         np.testing.assert_allclose(np.sqrt(st.information / N), g[name + "/logZ_err"], rtol=1e-11)
 
 
-@pytest.mark.parametrize("multipass", ["sorted", "radix", "multipass"])
+@pytest.mark.parametrize("multipass", ["cluster", "sorted", "radix", "multipass"])
 @pytest.mark.parametrize("k", [1, 7, 32])
 def test_outer_loop_replay_batched_matches_oracle(cuda, golden_dir, k, multipass):
     from gleipnir_b200 import likelihoods as lk
@@ -119,7 +119,7 @@ def _mk(kind, d):
     return lk.Mixture1DLogLikelihood(), Model("mixture1d", 1, positions=[0.1, 0.2, 0.5, 0.55, 0.9, 1.1], width=0.01)
 
 
-@pytest.mark.parametrize("multipass", ["sorted", "radix", "multipass"])
+@pytest.mark.parametrize("multipass", ["cluster", "sorted", "radix", "multipass"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_whole_run_matches_oracle_engine(cuda, case, multipass):
     """Same Philox counters on both sides -> the CUDA engine and the CPU restatement must
@@ -276,15 +276,37 @@ def test_fused_and_multipass_kill_agree_at_the_size_limit(cuda):
     like = lk.EggCartonLogLikelihood(2)
     N, k, n_deaths = 24576, 3000, 9000
     out = []
-    for mp in ("radix", "multipass"):
+    for mp in ("radix", "multipass", "cluster"):
         eng = _engine(table, like, N, k, n_deaths, multipass=mp, seed=3, iterations=5, tuning_cycles=1)
+        eng.init(); eng.advance(n_deaths); eng.finalize()
+        tab, idx, _ = eng.dead_table()
+        st = eng.state()
+        out.append((tab, idx, st.log_z, st.information, st.n_launches))
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0]) and np.array_equal(out[0][1], o[1])
+        assert out[0][2] == o[2] and out[0][3] == o[3]
+    assert out[0][4] < out[1][4]          # the fused path really launched fewer kernels
+    assert out[2][4] == out[0][4]
+
+
+def test_cluster_kill_serves_populations_beyond_one_cta(cuda):
+    """N = 100 000 (> 24 576): the 8-CTA cluster kill (one launch per step) against the multi-launch
+    path, bit for bit, including ties (a likelihood plateau of -inf outside the prior box is not
+    reachable here, so ties are planted through a 1-D mixture's flushed tails)."""
+    from gleipnir_b200 import likelihoods as lk
+    table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * 2
+    like = lk.EggCartonLogLikelihood(2)
+    N, k, n_deaths = 100000, 20000, 50000
+    out = []
+    for mp in ("cluster", "multipass"):
+        eng = _engine(table, like, N, k, n_deaths, multipass=mp, seed=5, iterations=2, tuning_cycles=0)
         eng.init(); eng.advance(n_deaths); eng.finalize()
         tab, idx, _ = eng.dead_table()
         st = eng.state()
         out.append((tab, idx, st.log_z, st.information, st.n_launches))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
-    assert out[0][4] < out[1][4]          # the fused path really launched fewer kernels
+    assert out[0][4] < out[1][4]
 
 
 @pytest.mark.parametrize("name,seed,d,N,skw,n_iter", [
@@ -436,7 +458,7 @@ def test_sorted_radix_and_multipass_paths_are_bit_identical(cuda):
     like = lk.EggCartonLogLikelihood(2)
     N, k, n_deaths = 16384, 1500, 7000
     out = []
-    for mp in ("sorted", "radix", "multipass"):
+    for mp in ("cluster", "sorted", "radix", "multipass"):
         eng = _engine(table, like, N, k, n_deaths, multipass=mp, seed=11, iterations=4, tuning_cycles=1)
         eng.init(); eng.advance(3000); eng.advance(n_deaths); eng.finalize()
         tab, idx, _ = eng.dead_table()
