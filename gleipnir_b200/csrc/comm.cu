@@ -96,6 +96,7 @@ extern "C" int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_lo
                                             int32_t k, int32_t m, void *keys_scratch, void *stream);
 extern "C" int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas);
 extern "C" int64_t gl_ns_local_population(const gl_ns *ns);
+extern "C" void gl_ns_internal_sharded_loop(gl_ns *ns, int on);
 
 extern "C" {
 
@@ -159,6 +160,11 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
     const int64_t n_local = gl_ns_local_population(ns);
     int64_t done = n_dead_so_far;
     bool first = true;
+    struct LoopGuard {                       // refills inside this loop leave their epilogue to the candidates kernel
+        gl_ns *ns;
+        explicit LoopGuard(gl_ns *p) : ns(p) { gl_ns_internal_sharded_loop(ns, 1); }
+        ~LoopGuard() { gl_ns_internal_sharded_loop(ns, 0); }
+    } guard(ns);
     while (done < n_deaths_total) {
         const int32_t k = (int32_t)((n_deaths_total - done) < batch_k ? (n_deaths_total - done) : batch_k);
         if (!first || n_dead_so_far > 0) {

@@ -712,64 +712,35 @@ __device__ __forceinline__ double block_max_v2(double a, double b, double *scrat
     return scratch[32];
 }
 
-__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) kill_cluster_kernel(
-    EngineState *S, int end_walk_tc, long long evals_per_walker, int k_req, long long n_target, int N, int d,
-    long long row_offset, double n_global, long long capacity, const double *__restrict__ live,
-    const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
-    double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
-    long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+struct ClusterSelSmem {                         // static shared memory of a cluster-select kernel
+    ClusterXchg X;
+    unsigned int wh[KC_NW * 8];                 // per-warp packed digit counts / lt,eq counts
+    unsigned int tot[16];
+    unsigned long long mm[2 * KC_NW];
+    unsigned long long bc[4];                   // broadcast slots
+};
+
+// Cluster-wide selection of the k smallest of `n` ordering keys under (key, index) order.  CTA c
+// holds the keys of global indices [c*Nc, c*Nc + n_loc) in `keys` (its shared memory), Nc =
+// ceil(n / KC_CTAS).  The selected global indices go to out_list[0..k) ascending (global memory),
+// optionally flagged in is_dead; the largest selected key is returned to every thread of every
+// CTA.  On return (a cluster barrier has been passed) out_list is complete and visible
+// cluster-wide.  Same decisions as cta_select_kworst.
+__device__ unsigned long long cluster_select_kworst(cooperative_groups::cluster_group &cluster, ClusterSelSmem &sm,
+                                                    const unsigned long long *keys, int n, int k,
+                                                    long long *__restrict__ out_list,
+                                                    unsigned char *__restrict__ is_dead) {
     const int c = (int)cluster.block_rank();
-    extern __shared__ unsigned long long keys[];                 // this CTA's chunk of ordering keys
-    __shared__ ClusterXchg X;
-    __shared__ unsigned int wh[KC_NW * 8];                       // per-warp packed digit counts / lt,eq counts
-    __shared__ unsigned int tot[16];
-    __shared__ unsigned long long mm[2 * KC_NW];
-    __shared__ unsigned long long bc[4];                         // broadcast slots
-    __shared__ double scratch[33];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-    // ---- snapshot of the state every CTA needs (CTA 0 rewrites S only at the very end) -----------
-    const int kp = S->k_cur;
-    const int step_now = S->step + (end_walk_tc >= 0 ? 1 : 0);
-    const long long n_dead0 = S->n_dead, base_row = S->n_rows;
-    const double logX0 = S->logX, m_old = S->M;
-
-    // ---- epilogue of the previous refill (end_walk_kernel's job), spread over the cluster ---------
-    if (end_walk_tc >= 0) {
-        for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
-        if (c == 0) {
-            const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
-            __syncthreads();
-            if (tid < d) {
-                S->widths[tid] = wnew;
-                for (int q = 0; q < end_walk_tc; ++q) S->acc[q][tid] = 0u;
-            }
-        }
-    }
-    long long kk = n_target - n_dead0;
-    if (kk > k_req) kk = k_req;
-    if (kk > N - 1) kk = N - 1;
-    if (kk < 0) kk = 0;
-    const int k = (int)kk;
-    if (k <= 0) {
-        if (c == 0 && tid == 0) {
-            if (end_walk_tc >= 0) { S->n_evals += (unsigned long long)((long long)kp * evals_per_walker); S->step = step_now; }
-            S->k_cur = 0;
-            S->do_walk = 0;
-        }
-        return;
-    }
-
-    // ---- load this CTA's chunk --------------------------------------------------------------------
-    const int Nc = (N + KC_CTAS - 1) / KC_CTAS;
+    ClusterXchg &X = sm.X;
+    unsigned int *wh = sm.wh, *tot = sm.tot;
+    unsigned long long *mm = sm.mm, *bc = sm.bc;
+    const int Nc = (n + KC_CTAS - 1) / KC_CTAS;
     const int lo_g = c * Nc;
-    const int n_loc = N - lo_g < 0 ? 0 : (N - lo_g < Nc ? N - lo_g : Nc);
+    const int n_loc = n - lo_g < 0 ? 0 : (n - lo_g < Nc ? n - lo_g : Nc);
     unsigned long long kmin = ~0ull, kmax = 0ull;
     for (int i = tid; i < n_loc; i += KC_THREADS) {
-        const unsigned long long key = sort_key(logl[lo_g + i]);
-        keys[i] = key;
+        const unsigned long long key = keys[i];
         kmin = key < kmin ? key : kmin;
         kmax = key > kmax ? key : kmax;
     }
@@ -790,7 +761,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
         X.kmin = kmin;
         X.kmax = kmax;
     }
-    cluster.sync();                                              // (also: every is_dead clear above is done)
+    cluster.sync();
     if (wid == 0) {
         unsigned long long a = ~0ull, b2 = 0ull;
         if (lane < KC_CTAS) {
@@ -810,7 +781,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     kmin = bc[0];
     kmax = bc[1];
 
-    // ---- radix select, 4-bit digits (same decisions as cta_select_kworst) ---------------------------
+    // ---- radix select, 4-bit digits ---------------------------------------------------------------
     const unsigned long long diff = kmin ^ kmax;
     const int first_pass = diff ? __clzll((long long)diff) >> 2 : 16;
     unsigned long long prefix = first_pass ? kmin >> (64 - 4 * first_pass) : 0ull;
@@ -881,7 +852,6 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
         my_lt += __popc(__ballot_sync(0xffffffffu, i < hi && kh < T));
         my_eq += __popc(__ballot_sync(0xffffffffu, i < hi && kh == T));
     }
-    __syncthreads();                                             // wh: last pass's readers are done
     if (lane == 0) { wh[wid] = (unsigned)my_lt; wh[KC_NW + wid] = (unsigned)my_eq; }
     __syncthreads();
     if (tid == 0) {
@@ -916,8 +886,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
         const int eq_before = run_eq + __popc(b_eq & lanemask_lt);
         if (is_lt || (is_eq && eq_before < r_ties)) {
             const int pos = lt_before + (eq_before < r_ties ? eq_before : r_ties);
-            dead_list[pos] = lo_g + i;
-            is_dead[lo_g + i] = 1;
+            out_list[pos] = lo_g + i;
+            if (is_dead) is_dead[lo_g + i] = 1;
             kstar = key > kstar ? key : kstar;
         }
         run_lt += __popc(b_lt);
@@ -934,7 +904,116 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
         for (int w = 0; w < KC_NW; ++w) { const unsigned long long a = mm[w]; kstar = a > kstar ? a : kstar; }
         X.kstar = kstar;
     }
-    cluster.sync();                                              // dead_list complete and visible cluster-wide
+    cluster.sync();                                              // out_list complete and visible cluster-wide
+    if (wid == 0) {
+        unsigned long long a = lane < KC_CTAS ? cluster.map_shared_rank(&X, lane)->kstar : 0ull;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long a2 = __shfl_xor_sync(0xffffffffu, a, o);
+            a = a2 > a ? a2 : a;
+        }
+        if (lane == 0) bc[2] = a;
+    }
+    __syncthreads();
+    return bc[2];
+}
+
+// evidence / information update of one batch by ONE 512-thread CTA with the summation tree of the
+// 1024-thread kernels (accumulate_kernel, kill_small_kernel): L(i) = vals[idx[i]], i < k
+__device__ void cta_accumulate_v2(EngineState *S, const long long *__restrict__ idx, const double *__restrict__ vals,
+                                  int k, double logw, double w, double m_old, double *scratch, double &mx_out,
+                                  double &m_new_out, double (&sums)[4]) {
+    const int tid = threadIdx.x;
+    double mxa = -INFINITY, mxb = -INFINITY;
+    for (int i = tid; i < k; i += 2 * KC_THREADS) {
+        const double lw = logw + vals[idx[i]];
+        if (isfinite(lw)) mxa = fmax(mxa, lw);
+    }
+    for (int i = tid + KC_THREADS; i < k; i += 2 * KC_THREADS) {
+        const double lw = logw + vals[idx[i]];
+        if (isfinite(lw)) mxb = fmax(mxb, lw);
+    }
+    const double mx = block_max_v2(mxa, mxb, scratch);
+    const double m_new = fmax(m_old, mx);
+    double sz[2] = {0.0, 0.0}, sh[2] = {0.0, 0.0}, zl[2] = {0.0, 0.0}, hl[2] = {0.0, 0.0};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        for (int i = tid + v * KC_THREADS; i < k; i += 2 * KC_THREADS) {
+            const double L = vals[idx[i]];
+            const double lw = logw + L;
+            if (isfinite(lw)) {
+                const double t = exp(lw - m_new);
+                sz[v] += t;
+                sh[v] += t * L;
+            }
+            const double dZ = w * exp(L);
+            zl[v] += dZ;
+            const double dH = dZ * L;
+            if (dH == dH) hl[v] += dH;
+        }
+    }
+    sums[0] = block_sum_v2(sz[0], sz[1], scratch);
+    sums[1] = block_sum_v2(sh[0], sh[1], scratch);
+    sums[2] = block_sum_v2(zl[0], zl[1], scratch);
+    sums[3] = block_sum_v2(hl[0], hl[1], scratch);
+    mx_out = mx;
+    m_new_out = m_new;
+}
+
+__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) kill_cluster_kernel(
+    EngineState *S, int end_walk_tc, long long evals_per_walker, int k_req, long long n_target, int N, int d,
+    long long row_offset, double n_global, long long capacity, const double *__restrict__ live,
+    const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
+    double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
+    long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    extern __shared__ unsigned long long keys[];                 // this CTA's chunk of ordering keys
+    __shared__ ClusterSelSmem sm;
+    __shared__ double scratch[33];
+    const int tid = threadIdx.x;
+
+    // ---- snapshot of the state every CTA needs (CTA 0 rewrites S only at the very end) -----------
+    const int kp = S->k_cur;
+    const int step_now = S->step + (end_walk_tc >= 0 ? 1 : 0);
+    const long long n_dead0 = S->n_dead, base_row = S->n_rows;
+    const double logX0 = S->logX, m_old = S->M;
+
+    // ---- epilogue of the previous refill (end_walk_kernel's job), spread over the cluster ---------
+    if (end_walk_tc >= 0) {
+        for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
+        if (c == 0) {
+            const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
+            __syncthreads();
+            if (tid < d) {
+                S->widths[tid] = wnew;
+                for (int q = 0; q < end_walk_tc; ++q) S->acc[q][tid] = 0u;
+            }
+        }
+    }
+    long long kk = n_target - n_dead0;
+    if (kk > k_req) kk = k_req;
+    if (kk > N - 1) kk = N - 1;
+    if (kk < 0) kk = 0;
+    const int k = (int)kk;
+    if (k <= 0) {
+        if (c == 0 && tid == 0) {
+            if (end_walk_tc >= 0) { S->n_evals += (unsigned long long)((long long)kp * evals_per_walker); S->step = step_now; }
+            S->k_cur = 0;
+            S->do_walk = 0;
+        }
+        return;
+    }
+
+    // ---- this CTA's chunk of keys, cluster-wide selection ----------------------------------------------
+    const int Nc = (N + KC_CTAS - 1) / KC_CTAS;
+    const int lo_g = c * Nc;
+    const int n_loc = N - lo_g < 0 ? 0 : (N - lo_g < Nc ? N - lo_g : Nc);
+    for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(logl[lo_g + i]);
+    __syncthreads();
+    // (the first cluster barrier inside also orders every is_dead clear above before the new flags)
+    const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, N, k, dead_list, is_dead);
 
     // ---- record: rows spread over the cluster --------------------------------------------------------
     const double logw = logX0 - log(n_global + 1.0);
@@ -954,62 +1033,23 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
         }
     }
 
-    // ---- accumulate on CTA 0 (virtual 1024-thread tree: same bits as kill_small_kernel) ---------------
+    // ---- accumulate on CTA 0 ----------------------------------------------------------------------------
     if (c == 0) {
-        if (wid == 0) {
-            unsigned long long a = lane < KC_CTAS ? cluster.map_shared_rank(&X, lane)->kstar : 0ull;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const unsigned long long a2 = __shfl_xor_sync(0xffffffffu, a, o);
-                a = a2 > a ? a2 : a;
-            }
-            if (lane == 0) bc[2] = a;
-        }
-        double mxa = -INFINITY, mxb = -INFINITY;
-        for (int i = tid; i < k; i += 2 * KC_THREADS) {
-            const double lw = logw + logl[dead_list[i]];
-            if (isfinite(lw)) mxa = fmax(mxa, lw);
-        }
-        for (int i = tid + KC_THREADS; i < k; i += 2 * KC_THREADS) {
-            const double lw = logw + logl[dead_list[i]];
-            if (isfinite(lw)) mxb = fmax(mxb, lw);
-        }
-        const double mx = block_max_v2(mxa, mxb, scratch);
-        const double m_new = fmax(m_old, mx);
-        double sz[2] = {0.0, 0.0}, sh[2] = {0.0, 0.0}, zl[2] = {0.0, 0.0}, hl[2] = {0.0, 0.0};
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            for (int i = tid + v * KC_THREADS; i < k; i += 2 * KC_THREADS) {
-                const double L = logl[dead_list[i]];
-                const double lw = logw + L;
-                if (isfinite(lw)) {
-                    const double t = exp(lw - m_new);
-                    sz[v] += t;
-                    sh[v] += t * L;
-                }
-                const double dZ = w * exp(L);
-                zl[v] += dZ;
-                const double dH = dZ * L;
-                if (dH == dH) hl[v] += dH;
-            }
-        }
-        const double szs = block_sum_v2(sz[0], sz[1], scratch);
-        const double shs = block_sum_v2(sh[0], sh[1], scratch);
-        const double zls = block_sum_v2(zl[0], zl[1], scratch);
-        const double hls = block_sum_v2(hl[0], hl[1], scratch);
+        double mx, m_new, sums[4];
+        cta_accumulate_v2(S, dead_list, logl, k, logw, w, m_old, scratch, mx, m_new, sums);
         if (tid == 0) {
             if (mx > -INFINITY) {
                 const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
-                S->Zs = S->Zs * scale + szs;
-                S->Hs = S->Hs * scale + shs;
+                S->Zs = S->Zs * scale + sums[0];
+                S->Hs = S->Hs * scale + sums[1];
                 S->M = m_new;
             }
-            S->Z_lin += zls;
-            S->H_lin += hls;
+            S->Z_lin += sums[2];
+            S->H_lin += sums[3];
             S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
             S->n_dead = n_dead0 + k;
             if (room) S->n_rows = base_row + k;
-            S->lstar = key_to_double(bc[2]);
+            S->lstar = key_to_double(kstar);
             S->k_cur = k;
             S->do_walk = n_dead0 + k < n_target;
             if (end_walk_tc >= 0) {
@@ -1021,119 +1061,119 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     cluster.sync();                                              // nobody exits while its mailbox may still be read
 }
 
-// ---- fused single-CTA kernels of the sharded step (local N and world*k both <= KILL_SMALL_MAX_N) --
-// candidates: this rank's k worst slots (ascending slot order) and their logL, one launch
-__global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_candidates_small_kernel(
-    const double *__restrict__ logl, int N, int k, long long *__restrict__ cand_list, double *__restrict__ cand_logl) {
+// ---- sharded step on a cluster: candidates and commit ---------------------------------------------
+__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) shard_candidates_cluster_kernel(
+    EngineState *S, int end_walk_tc /* >= 0: first finish the previous refill */, long long evals_per_walker, int d,
+    const long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead, const double *__restrict__ logl, int N,
+    int m, long long *__restrict__ cand_list, double *__restrict__ cand_logl) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
     extern __shared__ unsigned long long keys[];
-    __shared__ unsigned int hist[SEL_BINS];
+    __shared__ ClusterSelSmem sm;
     const int tid = threadIdx.x;
-    for (int i = tid; i < N; i += KILL_SMALL_THREADS) keys[i] = sort_key(logl[i]);
+    const int kp = S->k_cur;
+    if (end_walk_tc >= 0) {                                      // end_walk_kernel's job, spread over the cluster
+        for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
+        if (c == 0) {
+            const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
+            __syncthreads();
+            if (tid < d) {
+                S->widths[tid] = wnew;
+                for (int q = 0; q < end_walk_tc; ++q) S->acc[q][tid] = 0u;
+            }
+        }
+    }
+    const int Nc = (N + KC_CTAS - 1) / KC_CTAS;
+    const int lo_g = c * Nc;
+    const int n_loc = N - lo_g < 0 ? 0 : (N - lo_g < Nc ? N - lo_g : Nc);
+    for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(logl[lo_g + i]);
     __syncthreads();
-    (void)cta_select_kworst(keys, N, k, hist, cand_list, nullptr);
-    __syncthreads();
-    for (int i = tid; i < k; i += KILL_SMALL_THREADS) cand_logl[i] = logl[cand_list[i]];
+    (void)cluster_select_kworst(cluster, sm, keys, N, m, cand_list, nullptr);
+    for (int i = c * KC_THREADS + tid; i < m; i += KC_CTAS * KC_THREADS) cand_logl[i] = logl[cand_list[i]];
+    if (end_walk_tc >= 0 && c == 0 && tid == 0) {                // every CTA read S->k_cur before the first barrier
+        S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
+        S->step += 1;
+        S->do_walk = 0;
+        S->k_cur = 0;
+    }
+    cluster.sync();
 }
 
-// commit: global selection over the gathered [world*k] candidates, translation of this rank's
-// share to local slots, dead-row record and the (redundant, identical on every rank) evidence
-// update -- one launch.  Same forms as shard_local_kernel + record_kernel + accumulate_kernel.
-__global__ void __launch_bounds__(KILL_SMALL_THREADS) shard_commit_small_kernel(
+__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) shard_commit_cluster_kernel(
     EngineState *S, const double *__restrict__ gathered, int world, int rank, int k, int m, int d, long long row_offset,
     double n_global, long long capacity, const long long *__restrict__ cand_list, long long *__restrict__ positions,
     const double *__restrict__ live, const double *__restrict__ logl, long long *__restrict__ dead_list,
     unsigned char *__restrict__ is_dead, double *__restrict__ dead_x, double *__restrict__ dead_logl,
-    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step,
-    unsigned long long *keys_global /* scratch for world*k keys when they do not fit in shared memory */) {
-    extern __shared__ unsigned long long keys_smem[];
-    unsigned long long *keys = keys_global ? keys_global : keys_smem;
-    __shared__ unsigned int hist[SEL_BINS];
+    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    extern __shared__ unsigned long long keys[];
+    __shared__ ClusterSelSmem sm;
     __shared__ double scratch[33];
     __shared__ int s_start, s_end;
     const int tid = threadIdx.x;
+    const long long n_dead0 = S->n_dead, base_row = S->n_rows;
+    const int step_now = S->step;
+    const double logX0 = S->logX, m_old = S->M;
     const int n = world * m;
-    for (int i = tid; i < n; i += KILL_SMALL_THREADS) keys[i] = sort_key(gathered[i]);
+    const int Nc = (n + KC_CTAS - 1) / KC_CTAS;
+    const int lo_g = c * Nc;
+    const int n_loc = n - lo_g < 0 ? 0 : (n - lo_g < Nc ? n - lo_g : Nc);
+    for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(gathered[lo_g + i]);
     __syncthreads();
-    const unsigned long long kstar = cta_select_kworst(keys, n, k, hist, positions, nullptr);
-    __syncthreads();
-    if (m < k && tid >= 32 && tid < 32 + world && shard_exchange_overflowed(positions, k, m, tid - 32)) S->shard_overflow = 1;
-    if (tid == 0) {
-        const long long lo_pos = (long long)rank * m, hi_pos = lo_pos + m;
-        int a = 0, b = k;
-        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < lo_pos) a = m + 1; else b = m; }
-        s_start = a;
-        b = k;
-        while (a < b) { const int m = (a + b) >> 1; if (positions[m] < hi_pos) a = m + 1; else b = m; }
-        s_end = a;
+    const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, n, k, positions, nullptr);
+    if (c == 0 && m < k && tid >= 32 && tid < 32 + world && shard_exchange_overflowed(positions, k, m, tid - 32))
+        S->shard_overflow = 1;
+    if (tid == 0) {                                              // this rank's contiguous share of `positions`
+        s_start = lower_bound_pos(positions, k, (long long)rank * m);
+        s_end = lower_bound_pos(positions, k, (long long)(rank + 1) * m);
     }
     __syncthreads();
-    const int start = s_start, n_loc = s_end - s_start;
-    for (int i = tid; i < n_loc; i += KILL_SMALL_THREADS) {
+    const int start = s_start, n_own = s_end - s_start;
+    const double logw = logX0 - log(n_global + 1.0);
+    const double w = exp(logw);
+    const bool room = base_row + n_own <= capacity;
+    for (int i = c * KC_THREADS + tid; i < n_own; i += KC_CTAS * KC_THREADS) {
         const long long slot = cand_list[positions[start + i] - (long long)rank * m];
         dead_list[i] = slot;
         is_dead[slot] = 1;
+        if (room) {
+            dead_logl[base_row + i] = logl[slot];
+            dead_w[base_row + i] = w;
+            dead_idx[base_row + i] = slot + row_offset;
+            dead_step[base_row + i] = step_now;
+        }
     }
-    __syncthreads();
-    const long long base_row = S->n_rows;
-    const double logw = S->logX - log(n_global + 1.0);
-    const double w = exp(logw);
-    const bool room = base_row + n_loc <= capacity;
     if (room) {
-        const int step = S->step;
-        for (int e = tid; e < n_loc * d; e += KILL_SMALL_THREADS) {
+        for (int e = c * KC_THREADS + tid; e < n_own * d; e += KC_CTAS * KC_THREADS) {
             const int q = e / d, j = e - q * d;
-            const long long slot = dead_list[q];
+            const long long slot = cand_list[positions[start + q] - (long long)rank * m];
             dead_x[(base_row + q) * d + j] = live[slot * d + j];
-            if (j == 0) {
-                dead_logl[base_row + q] = logl[slot];
-                dead_w[base_row + q] = w;
-                dead_idx[base_row + q] = slot + row_offset;
-                dead_step[base_row + q] = step;
+        }
+    }
+    if (c == 0) {
+        double mx, m_new, sums[4];
+        cta_accumulate_v2(S, positions, gathered, k, logw, w, m_old, scratch, mx, m_new, sums);
+        if (tid == 0) {
+            if (mx > -INFINITY) {
+                const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+                S->Zs = S->Zs * scale + sums[0];
+                S->Hs = S->Hs * scale + sums[1];
+                S->M = m_new;
             }
+            S->Z_lin += sums[2];
+            S->H_lin += sums[3];
+            S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
+            S->n_dead = n_dead0 + k;
+            if (room) S->n_rows = base_row + n_own;
+            S->lstar = key_to_double(kstar);
+            S->k_cur = n_own;
+            S->do_walk = 1;
         }
     }
-    double mx = -INFINITY;
-    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
-        const double lw = logw + gathered[positions[i]];
-        if (isfinite(lw)) mx = fmax(mx, lw);
-    }
-    mx = block_max(mx, scratch);
-    const double m_old = S->M;
-    const double m_new = fmax(m_old, mx);
-    double sz = 0.0, sh = 0.0, zl = 0.0, hl = 0.0;
-    for (int i = tid; i < k; i += KILL_SMALL_THREADS) {
-        const double L = gathered[positions[i]];
-        const double lw = logw + L;
-        if (isfinite(lw)) {
-            const double t = exp(lw - m_new);
-            sz += t;
-            sh += t * L;
-        }
-        const double dZ = w * exp(L);
-        zl += dZ;
-        const double dH = dZ * L;
-        if (dH == dH) hl += dH;
-    }
-    sz = block_sum(sz, scratch);
-    sh = block_sum(sh, scratch);
-    zl = block_sum(zl, scratch);
-    hl = block_sum(hl, scratch);
-    if (tid == 0) {
-        if (mx > -INFINITY) {
-            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
-            S->Zs = S->Zs * scale + sz;
-            S->Hs = S->Hs * scale + sh;
-            S->M = m_new;
-        }
-        S->Z_lin += zl;
-        S->H_lin += hl;
-        S->logX += log((n_global - (double)k + 1.0) / (n_global + 1.0));
-        S->n_dead += k;
-        if (room) S->n_rows += n_loc;
-        S->lstar = key_to_double(kstar);
-        S->k_cur = n_loc;
-        S->do_walk = 1;
-    }
+    cluster.sync();
 }
 
 // ---- end of refill: clear the dead flags, persist widths, advance the step ----------------
@@ -1438,7 +1478,8 @@ struct gl_ns {
     bool prof;
     bool force_multipass;                         // tests: exercise the multi-launch select path
     bool end_walk_deferred;                       // last refill's epilogue is still to run
-    bool defer_ok;                                // inside gl_ns_advance: the next op is a kill
+    bool defer_ok;                                // inside gl_ns_advance(_sharded): the next op is a kill / candidates
+    bool sharded_loop;                            // inside gl_ns_advance_sharded
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -1549,16 +1590,29 @@ static int flush_end_walk(gl_ns *ns, cudaStream_t st) {
     return end_walk_launch(ns, st, (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d);
 }
 
+// Which kill the next gl_ns_kill uses: 1 multi-launch, 2 fused single-CTA radix, 3 fused sorted, 4 cluster.
+// auto = cluster: at N = 10^4, k = 10^3 a kill measures 24.5 us on the 8-CTA cluster against 36 us for
+// the single-CTA radix kernel and 52 us for the sorted-merge variant (a 1024-entry bitonic sort alone
+// is ~43 k warp-instructions on the one SM that runs it); the cluster also serves N up to 196 608.
+static int kill_variant(const gl_ns *ns) {
+    const long long N = ns->cfg.population_size;
+    const int path = ns->force_multipass ? 1 : ns->select_path;
+    if (path == 3 && N <= SORTED_MAX_N) return 3;
+    if ((path == 0 || path == 4) && N <= KC_MAX_N) return 4;
+    if (path != 1 && N <= KILL_SMALL_MAX_N) return 2;
+    return 1;
+}
+// the op that follows a refill inside the native loops folds end_walk_kernel into its prologue
+static bool next_op_folds_end_walk(const gl_ns *ns) {
+    if (ns->sharded_loop) return ns->cfg.population_size <= KC_MAX_N && !ns->force_multipass;
+    return kill_variant(ns) != 1;
+}
+
 static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st) {
     const long long N = ns->cfg.population_size;
     const double n_global = (double)ns->cfg.global_population;
-    const int path = ns->force_multipass ? 1 : ns->select_path;
-    // auto = fused radix: measured 37 us per kill at N = 10^4, k = 10^3 against 52 us for the sorted-merge
-    // variant (a 1024-entry bitonic sort alone is ~43 k warp-instructions on the one SM that runs the kill)
-    // and 36 us -> ?? for the 8-CTA cluster version (path 4), which also serves N up to 196 608 in one launch
-    const bool use_sorted = path == 3 && N <= SORTED_MAX_N;
-    const bool use_cluster = !use_sorted && (path == 0 || path == 4) && N <= KC_MAX_N;
-    const bool use_radix = !use_sorted && !use_cluster && (path == 0 || path == 2 || path == 3 || path == 4) && N <= KILL_SMALL_MAX_N;
+    const int variant = kill_variant(ns);
+    const bool use_sorted = variant == 3, use_cluster = variant == 4, use_radix = variant == 2;
     if (use_sorted || use_radix || use_cluster) {
         const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
         ns->end_walk_deferred = false;
@@ -1644,8 +1698,8 @@ static int refill_launch(gl_ns *ns, cudaStream_t st) {
     prof_mark(ns, ns->ev_walk, st);
     ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
     ns->h_launches += ns->cfg.tuning_cycles + 1;
-    if (ns->defer_ok && ns->cfg.population_size <= KILL_SMALL_MAX_N && !ns->force_multipass && ns->select_path != 1) {
-        ns->end_walk_deferred = true;      // the next kill_small_kernel finishes this refill
+    if (ns->defer_ok && next_op_folds_end_walk(ns)) {
+        ns->end_walk_deferred = true;      // the next fused kill / candidates kernel finishes this refill
         ns->h_step += 1;
         ns->pending_refill = false;
         return GL_OK;
@@ -1713,6 +1767,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->force_multipass = false;
     ns->end_walk_deferred = false;
     ns->defer_ok = false;
+    ns->sharded_loop = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
@@ -1921,18 +1976,24 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
     cudaStream_t st = (cudaStream_t)stream;
     const long long N = ns->cfg.population_size;
     gl::prof_mark(ns, ns->ev_sel, st);
-    if (N <= gl::KILL_SMALL_MAX_N && !ns->force_multipass) {
-        int rc = gl::ensure_smem((const void *)gl::shard_candidates_small_kernel, (int)(8 * N));
+    if (N <= gl::KC_MAX_N && !ns->force_multipass) {
+        const int smem = (int)(8 * ((N + gl::KC_CTAS - 1) / gl::KC_CTAS));
+        int rc = gl::ensure_smem((const void *)gl::shard_candidates_cluster_kernel, smem);
         if (rc) return rc;
-        gl::shard_candidates_small_kernel<<<1, gl::KILL_SMALL_THREADS, (int)(8 * N), st>>>(ns->buf.logl, (int)N, k,
-                                                                                          ns->cand_list, cand_logl_dev);
+        const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
+        ns->end_walk_deferred = false;
+        const long long epw = (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
+        gl::shard_candidates_cluster_kernel<<<gl::KC_CTAS, gl::KC_THREADS, smem, st>>>(
+            ns->S, tc_arg, epw, ns->d, ns->dead_list, ns->is_dead, ns->buf.logl, (int)N, k, ns->cand_list, cand_logl_dev);
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;
         ns->h_launches += 1;
         return GL_OK;
     }
-    int rc = gl::select_launch(ns->buf.logl, N, nullptr, k, 0, ns->cand_list, nullptr, nullptr, ns->sel, st);
+    int rc = gl::flush_end_walk(ns, st);
+    if (rc) return rc;
+    rc = gl::select_launch(ns->buf.logl, N, nullptr, k, 0, ns->cand_list, nullptr, nullptr, ns->sel, st);
     if (rc) return rc;
     gl::prof_mark(ns, ns->ev_sel, st);
     ns->prof_sel_launches += gl::SEL_PASSES + 2;
@@ -1957,6 +2018,12 @@ int gl_ns_shard_commit_scratch(gl_ns *ns, const double *gathered_logl_dev, int32
 
 int64_t gl_ns_local_population(const gl_ns *ns) { return ns ? ns->cfg.population_size : 0; }
 
+// comm.cu's loop: every refill it issues is followed by gl_ns_shard_candidates (not part of the ABI)
+void gl_ns_internal_sharded_loop(gl_ns *ns, int on) {
+    ns->sharded_loop = on != 0;
+    ns->defer_ok = on != 0;
+}
+
 int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas) {
     if (k < 1 || world < 1 || n_local < 2) return 0;
     long long m = k;
@@ -1979,21 +2046,19 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
     GL_REQUIRE(m >= 1 && m <= k && (long long)m * world >= k, "candidates per rank m=%d outside [ceil(k/world), k]", m);
     cudaStream_t st = (cudaStream_t)stream;
     const double n_global = (double)ns->cfg.global_population;
-    // 8-bit per-thread digit counters bound the single-CTA selection to 24 keys/thread in shared
-    // memory; with the keys in an L2-resident global scratch the same kernel serves world*k up to
-    // 255 keys/thread.
-    const bool fits_smem = (long long)world * m <= gl::KILL_SMALL_MAX_N;
-    const bool fits_global = keys_scratch != nullptr && (long long)world * m <= 255LL * gl::KILL_SMALL_THREADS;
-    if ((fits_smem || fits_global) && !ns->force_multipass) {
-        const int smem = fits_smem ? 8 * world * m : 0;
-        int rc0 = gl::ensure_smem((const void *)gl::shard_commit_small_kernel, smem);
+    (void)keys_scratch;                    // (kept in the ABI; the cluster commit holds its keys in shared memory)
+    if ((long long)world * m <= gl::KC_MAX_N && world <= gl::KC_THREADS - 32 && !ns->force_multipass) {
+        const int smem = (int)(8 * (((long long)world * m + gl::KC_CTAS - 1) / gl::KC_CTAS));
+        int rc0 = gl::ensure_smem((const void *)gl::shard_commit_cluster_kernel, smem);
         if (rc0) return rc0;
-        gl::shard_commit_small_kernel<<<1, gl::KILL_SMALL_THREADS, smem, st>>>(
+        gl::prof_mark(ns, ns->ev_sel, st);
+        gl::shard_commit_cluster_kernel<<<gl::KC_CTAS, gl::KC_THREADS, smem, st>>>(
             ns->S, gathered_logl_dev, world, rank, k, m, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
             ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
-            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step,
-            fits_smem ? nullptr : (unsigned long long *)keys_scratch);
+            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
         GL_CHECK_LAUNCH();
+        gl::prof_mark(ns, ns->ev_sel, st);
+        ns->prof_sel_launches += 1;
         ns->h_launches += 1;
         ns->h_n_dead += k;
         ns->h_k_last = -1;
