@@ -1480,6 +1480,7 @@ struct gl_ns {
     bool end_walk_deferred;                       // last refill's epilogue is still to run
     bool defer_ok;                                // inside gl_ns_advance(_sharded): the next op is a kill / candidates
     bool sharded_loop;                            // inside gl_ns_advance_sharded
+    bool force_smem_walker;                       // tests: generic shared-memory walker even for small d
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -1554,6 +1555,7 @@ static WalkParams walk_params(const gl_ns *ns) {
     P.proposal = ns->cfg.proposal;
     P.k_max = ns->cfg.batch_k;
     P.lanes = ns->cfg.walker_lanes;
+    P.force_smem_state = ns->force_smem_walker ? 1 : 0;
     return P;
 }
 
@@ -1768,6 +1770,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->end_walk_deferred = false;
     ns->defer_ok = false;
     ns->sharded_loop = false;
+    ns->force_smem_walker = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
@@ -2212,6 +2215,12 @@ int gl_ns_set_select_path(gl_ns *ns, int32_t path) {
                "path must be 0 (auto), 1 (multi-launch), 2 (fused radix), 3 (fused sorted), 4 (cluster radix)");
     GL_REQUIRE(!ns->h_sorted_ready || path == 0 || path == 3, "cannot leave the sorted path once the run has started");
     ns->select_path = path;
+    return GL_OK;
+}
+
+int gl_ns_force_smem_walker(gl_ns *ns, int32_t enable) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    ns->force_smem_walker = enable != 0;
     return GL_OK;
 }
 

@@ -48,6 +48,7 @@ struct WalkParams {                  // by-value kernel parameter
     uint64_t seed;
     int d, iterations, burn_in, tuning_cycles, proposal, k_max;
     int lanes;                       // lanes per walker (0 = choose from k_max)
+    int force_smem_state;            // tests: use the generic shared-memory walker even for small d
 };
 
 // walker.cu

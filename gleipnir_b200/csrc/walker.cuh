@@ -190,6 +190,170 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkParams P, ModelD
     }
 }
 
+// ---- register-resident walker for small d ------------------------------------------------------
+// The r01_g profile of walk_kernel at d = 2 shows a round of ~170 dependent, in-order-issued
+// instructions at ~8.6 cycles each, more than half of them shared-memory address arithmetic,
+// LDS/STS round trips of the walker state and runtime-d loop control.  For d <= REG_MAX_D the
+// point, the likelihood cache, widths and prior rows live in REGISTERS, replicated in every lane
+// of the group (commit = a shuffle from the accepting lane; no store, no group barrier), and d is
+// a template parameter.  Same moves, same arithmetic, same Philox counters: results are
+// bit-identical to walk_kernel (tests compare them).
+template <int D>
+__device__ __forceinline__ double reg_sel(const double (&a)[D], int j) {
+    double r = a[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) r = j == i ? a[i] : r;
+    return r;
+}
+
+template <class Like, int D, bool FULL>
+__global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, ModelDev M, int phase, int lgG) {
+    extern __shared__ double sm[];                 // step[WPB][CH] | u[WPB][CH]
+    __shared__ unsigned int acc_s[D];
+    EngineState *S = P.S;
+    if (!S->do_walk) return;                       // grid-uniform
+    const int k = S->k_cur;
+    const int G = FULL ? 32 : (1 << lgG);
+    const int WPB = WALK_THREADS >> lgG;
+    if (blockIdx.x * WPB >= k) return;             // block-uniform
+    const int CH = walker_chunk(G);
+    double *sbuf = sm;
+    double *ubuf = sm + (size_t)WPB * CH;
+    const int tid = threadIdx.x;
+    const bool tuning = phase < P.tuning_cycles;
+    if (tid < D) acc_s[tid] = 0u;
+    double wv[D], hw[D], p0v[D], p1v[D];
+    int kindv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        wv[j] = phase_width(S, j, phase, k);
+        hw[j] = -0.5 * wv[j];
+        p0v[j] = P.priors->p0[j];
+        p1v[j] = P.priors->p1[j];
+        kindv[j] = P.priors->kind[j];
+    }
+    __syncthreads();
+
+    const int wl = tid >> lgG;
+    const int lane = tid & (G - 1);
+    const int w = blockIdx.x * WPB + wl;
+    const bool active = w < k;                     // group-uniform
+    const unsigned gbase = FULL ? 0u : (unsigned)((tid & 31) & ~(G - 1));
+    const unsigned gmask = FULL ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    double *sb = sbuf + (size_t)wl * CH;
+    double *ub = ubuf + (size_t)wl * CH;
+    const Like like(M);
+    const double lstar = S->lstar;
+    const uint32_t step = (uint32_t)S->step;
+
+    if (active) {
+        const long long slot = P.dead_list[w];
+        const uint32_t g = (uint32_t)(slot + P.row_offset);
+        double x[D], c[D];
+        if (phase == 0 || !tuning) {
+            long long pick = 0;
+            if (lane == 0) {
+                for (uint32_t a = 0;; ++a) {       // survivor pick, redraw while dead
+                    const U2 u = philox_uniforms(P.seed, g, step, a, GL_TAG_PICK);
+                    pick = (long long)(u.a * (double)P.N);
+                    if (pick >= P.N) pick = P.N - 1;
+                    if (!P.is_dead[pick]) break;
+                }
+            }
+            pick = __shfl_sync(gmask, pick, gbase);
+            const double *src = P.live + pick * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = src[j];
+        } else {
+            const double *src = P.scratch_x + (size_t)w * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = src[j];
+        }
+        double L = like.template init_reg<D>(x, c);
+        unsigned int accr[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) accr[j] = 0u;
+
+        const int n_moves = (tuning ? 20 : P.iterations + P.burn_in) * D;
+        const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * D);
+        const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
+        int m = 0, base = -CH;                     // ring holds moves [base, base+CH)
+        while (m < n_moves) {                      // group-uniform
+            if (m + G > base + CH) {
+                base = m;
+                __syncwarp(gmask);
+                for (int q = lane; q < CH; q += G) {
+                    const int mv = base + q;
+                    if (mv < n_moves) {
+                        const int jj = (int)((uint32_t)mv % (uint32_t)D);
+                        const U2 ru = philox_uniforms(P.seed, g, step, c2_base + (uint32_t)mv, GL_TAG_MOVE);
+                        sb[q] = __dmul_rn(normal ? normcdfinv(ru.a) : ru.a, reg_sel<D>(wv, jj));
+                        ub[q] = ru.b;
+                    }
+                }
+                __syncwarp(gmask);
+            }
+            const int mine = m + lane;
+            bool ok = false;
+            double nj = 0.0, Lt = 0.0, cnew = 0.0;
+            if (mine < n_moves) {
+                const int j = (int)((uint32_t)mine % (uint32_t)D);
+                const double xj = reg_sel<D>(x, j);
+                // uniform: r*w + (x - w/2)   normal: ndtri(r)*w + x     (samplers.py:100,102)
+                const double loc = normal ? xj : __dadd_rn(xj, reg_sel<D>(hw, j));
+                nj = __dadd_rn(sb[mine - base], loc);
+                int kind = kindv[0];
+#pragma unroll
+                for (int i = 1; i < D; ++i) kind = j == i ? kindv[i] : kind;
+                if (prior_accept(kind, reg_sel<D>(p0v, j), reg_sel<D>(p1v, j), xj, nj, ub[mine - base])) {
+                    Lt = like.template trial_reg<D>(c, j, nj, cnew);
+                    ok = Lt > lstar;
+                }
+            }
+            const unsigned bal = __ballot_sync(gmask, ok) & gmask;
+            if (bal == 0u) {
+                m += G;
+                continue;
+            }
+            const int f = __ffs(bal) - 1;          // absolute lane of the first accept
+            const int fm = m + (f - (int)gbase);   // the accepted move; its component is group-uniform
+            const int jf = (int)((uint32_t)fm % (uint32_t)D);
+            nj = __shfl_sync(gmask, nj, f);
+            Lt = __shfl_sync(gmask, Lt, f);
+            cnew = __shfl_sync(gmask, cnew, f);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                if (jf == i) { x[i] = nj; c[i] = cnew; accr[i] += 1u; }
+            }
+            L = Lt;
+            m = fm + 1;
+        }
+
+        // ---- write back ----------------------------------------------------------------------
+        if (tuning) {
+            if (lane == 0) {
+                if (phase + 1 < P.tuning_cycles) {
+                    double *dst = P.scratch_x + (size_t)w * D;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) dst[j] = x[j];
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (accr[j]) atomicAdd(&acc_s[j], accr[j]);
+            }
+        } else if (lane == 0) {
+            double *dst = P.live + slot * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) dst[j] = x[j];
+            P.logl[slot] = L;
+        }
+    }
+    if (tuning) {
+        __syncthreads();
+        if (tid < D && acc_s[tid]) atomicAdd(&S->acc[phase][tid], acc_s[tid]);
+    }
+}
+
 inline int walker_smem_bytes(int d, int nc, int G) {
     const int WPB = WALK_THREADS / G;
     return (int)(sizeof(double) * ((size_t)(d + nc) * WPB + 2 * (size_t)WPB * walker_chunk(G) + 3 * (size_t)d) +
@@ -214,9 +378,34 @@ struct WalkLauncher {
     const WalkParams &P;
     const ModelDev &M;
     cudaStream_t st;
+    template <class Like, int D>
+    int launch_reg(int G) {
+        const int WPB = WALK_THREADS / G;
+        const int smem = (int)(sizeof(double) * 2 * (size_t)WPB * walker_chunk(G));
+        const int blocks = (P.k_max + WPB - 1) / WPB;
+        int lgG = 0;
+        while ((1 << lgG) < G) ++lgG;
+        for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
+            if (G == 32) walk_reg_kernel<Like, D, true><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+            else walk_reg_kernel<Like, D, false><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+        }
+        GL_CHECK_LAUNCH();
+        return GL_OK;
+    }
     template <class Like>
     int operator()() {
         int G = walker_group_size(P.k_max, P.lanes);
+        if constexpr (reg_max_d<Like>::value > 0) {
+            if (!P.force_smem_state && P.d <= reg_max_d<Like>::value) {
+                switch (P.d) {
+                    case 1: return launch_reg<Like, 1>(G);
+                    case 2: return launch_reg<Like, 2>(G);
+                    case 3: return launch_reg<Like, 3>(G);
+                    case 4: return launch_reg<Like, 4>(G);
+                    default: break;
+                }
+            }
+        }
         int smem = walker_smem_bytes(P.d, Like::cache_size(P.d), G);
         while (smem > 200 * 1024 && G < 32) {      // very large d: fewer walkers per block
             G *= 2;

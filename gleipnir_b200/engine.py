@@ -99,6 +99,10 @@ class DeviceEngine(object):
     def finalize(self):
         _lib.check(self.lib.gl_ns_finalize(self._h, self._stream()))
 
+    def force_smem_walker(self, enable=True):
+        """Use the generic shared-memory walker even where the register-resident one applies."""
+        _lib.check(self.lib.gl_ns_force_smem_walker(self._h, 1 if enable else 0))
+
     def force_multipass_select(self, enable=True):
         _lib.check(self.lib.gl_ns_force_multipass_select(self._h, 1 if enable else 0))
 

@@ -237,6 +237,40 @@ def test_reference_test_suite_flow(cuda):
         NS.evidence = 1.0
 
 
+@pytest.mark.parametrize("kind,d,proposal", [("egg", 1, 0), ("egg", 2, 0), ("egg", 2, 1), ("egg", 3, 0), ("egg", 4, 1),
+                                             ("iid", 2, 0), ("iid", 3, 1), ("iid", 4, 0)])
+def test_register_and_shared_memory_walkers_are_bit_identical(cuda, kind, d, proposal):
+    """d <= 4: the walker keeps its state in registers (walk_reg_kernel); it must retire exactly the
+    chain of the generic shared-memory walker -- mixed prior families, both proposal kinds, several
+    group sizes."""
+    like, _ = _mk(kind, d)
+    if kind == "egg":
+        table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
+    else:
+        rows = [(pr.GL_PRIOR_NORM, 0.0, 3.0), (pr.GL_PRIOR_UNIFORM, -5.0, 10.0), (pr.GL_PRIOR_LOGUNIFORM, 0.01, 5.0),
+                (pr.GL_PRIOR_NORM, 0.5, 2.0)]
+        table = rows[:d]
+    N, k, n_deaths = 300, 30, 600
+    ref = None
+    for lanes, smem in ((0, True), (0, False), (4, False), (1, False), (32, False)):
+        eng = _engine(table, like, N, k, n_deaths, seed=5, iterations=7, burn_in=1, tuning_cycles=2,
+                      walker_lanes=lanes, proposal=proposal)
+        if smem:
+            eng.force_smem_walker(True)
+        eng.init()
+        eng.advance(n_deaths)
+        eng.finalize()
+        tab, idx, _ = eng.dead_table()
+        st = eng.state()
+        cur = (tab, idx, st.log_z, st.information, np.array(st.widths[:d]), st.n_evals)
+        if ref is None:
+            ref = cur
+        else:
+            assert np.array_equal(cur[0], ref[0]) and np.array_equal(cur[1], ref[1]), (lanes, smem)
+            assert cur[2] == ref[2] and cur[3] == ref[3] and np.array_equal(cur[4], ref[4]), (lanes, smem)
+            assert cur[5] == ref[5]
+
+
 @pytest.mark.parametrize("kind,d", [("egg", 2), ("iid", 5), ("dense", 12)])
 def test_speculative_lanes_are_bit_identical(cuda, kind, d):
     """Speculative prefetch (G lanes per walker) must retire exactly the sequential chain:
