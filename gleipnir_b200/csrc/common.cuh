@@ -142,4 +142,29 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
     return scratch[32];
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A kernel launched with launch_pdl() may start while its predecessor in the stream is still
+// running; it must call pdl_wait() before touching anything the predecessor (or anything still in
+// flight before it) writes.  Protocol used throughout: pdl_wait() THEN pdl_trigger(), so a kernel
+// only lets its successor start once its own predecessor has completed -- the successor's
+// pre-wait code may therefore read data written two or more launches back, never newer.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace gl

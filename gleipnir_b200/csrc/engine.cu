@@ -973,6 +973,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     __shared__ ClusterSelSmem sm;
     __shared__ double scratch[33];
     const int tid = threadIdx.x;
+    pdl_wait();                                                  // launched with launch_pdl: the refill before us
+    pdl_trigger();                                               // must be complete; the next launch may queue up
 
     // ---- snapshot of the state every CTA needs (CTA 0 rewrites S only at the very end) -----------
     const int kp = S->k_cur;
@@ -1072,6 +1074,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     extern __shared__ unsigned long long keys[];
     __shared__ ClusterSelSmem sm;
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     const int kp = S->k_cur;
     if (end_walk_tc >= 0) {                                      // end_walk_kernel's job, spread over the cluster
         for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
@@ -1114,6 +1118,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     __shared__ double scratch[33];
     __shared__ int s_start, s_end;
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     const long long n_dead0 = S->n_dead, base_row = S->n_rows;
     const int step_now = S->step;
     const double logX0 = S->logX, m_old = S->M;
@@ -1637,10 +1643,10 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
             const int smem = (int)(sizeof(unsigned long long) * ((N + KC_CTAS - 1) / KC_CTAS));
             int rc0 = ensure_smem((const void *)kill_cluster_kernel, smem);
             if (rc0) return rc0;
-            kill_cluster_kernel<<<KC_CTAS, KC_THREADS, smem, st>>>(
-                ns->S, tc_arg, epw, k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global,
-                ns->cfg.dead_capacity, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
-                ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+            GL_CUDA(launch_pdl(kill_cluster_kernel, dim3(KC_CTAS), dim3(KC_THREADS), (size_t)smem, st, ns->S, tc_arg, epw,
+                               k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
+                               ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl,
+                               ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step));
         } else {
             const int smem = (int)(sizeof(unsigned long long) * N);
             int rc0 = ensure_smem((const void *)kill_small_kernel<false>, smem);
@@ -1986,8 +1992,9 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
         const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
         ns->end_walk_deferred = false;
         const long long epw = (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
-        gl::shard_candidates_cluster_kernel<<<gl::KC_CTAS, gl::KC_THREADS, smem, st>>>(
-            ns->S, tc_arg, epw, ns->d, ns->dead_list, ns->is_dead, ns->buf.logl, (int)N, k, ns->cand_list, cand_logl_dev);
+        GL_CUDA(gl::launch_pdl(gl::shard_candidates_cluster_kernel, dim3(gl::KC_CTAS), dim3(gl::KC_THREADS), (size_t)smem,
+                               st, ns->S, tc_arg, epw, ns->d, ns->dead_list, ns->is_dead, ns->buf.logl, (int)N, k,
+                               ns->cand_list, cand_logl_dev));
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;
@@ -2055,10 +2062,11 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
         int rc0 = gl::ensure_smem((const void *)gl::shard_commit_cluster_kernel, smem);
         if (rc0) return rc0;
         gl::prof_mark(ns, ns->ev_sel, st);
-        gl::shard_commit_cluster_kernel<<<gl::KC_CTAS, gl::KC_THREADS, smem, st>>>(
-            ns->S, gathered_logl_dev, world, rank, k, m, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
-            ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x,
-            ns->buf.dead_logl, ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step);
+        GL_CUDA(gl::launch_pdl(gl::shard_commit_cluster_kernel, dim3(gl::KC_CTAS), dim3(gl::KC_THREADS), (size_t)smem, st,
+                               ns->S, gathered_logl_dev, world, rank, k, m, ns->d, ns->cfg.row_offset, n_global,
+                               ns->cfg.dead_capacity, ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl,
+                               ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w,
+                               (long long *)ns->buf.dead_idx, ns->buf.dead_step));
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;

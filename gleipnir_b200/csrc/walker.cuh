@@ -208,31 +208,39 @@ __device__ __forceinline__ double reg_sel(const double (&a)[D], int j) {
 
 template <class Like, int D, bool FULL>
 __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, ModelDev M, int phase, int lgG) {
-    extern __shared__ double sm[];                 // step[WPB][CH] | u[WPB][CH]
+    extern __shared__ double sm[];                 // r[WPB][CH] | u[WPB][CH]: raw Philox uniforms of the ring
     __shared__ unsigned int acc_s[D];
     EngineState *S = P.S;
-    if (!S->do_walk) return;                       // grid-uniform
+    // PDL (common.cuh): phase 0 follows the kill/commit kernel whose outputs everything below
+    // needs, so it waits first.  Later phases follow the previous walker launch of the SAME
+    // refill: all they need from it are the pooled acceptance counts (-> widths) and the carried
+    // positions, so their whole state-independent prologue -- batch header, survivor pick, seed
+    // point, likelihood cache, the first ring of Philox uniforms -- runs BEFORE the wait and
+    // overlaps the tail of that launch.
+    const bool after_walk = phase > 0;
+    if (!after_walk) { pdl_wait(); pdl_trigger(); }
+    const bool do_walk = S->do_walk != 0;          // grid-uniform
     const int k = S->k_cur;
     const int G = FULL ? 32 : (1 << lgG);
     const int WPB = WALK_THREADS >> lgG;
-    if (blockIdx.x * WPB >= k) return;             // block-uniform
+    if (!do_walk || blockIdx.x * WPB >= k) {       // block-uniform
+        if (after_walk) { pdl_wait(); pdl_trigger(); }
+        return;
+    }
     const int CH = walker_chunk(G);
     double *sbuf = sm;
     double *ubuf = sm + (size_t)WPB * CH;
     const int tid = threadIdx.x;
     const bool tuning = phase < P.tuning_cycles;
     if (tid < D) acc_s[tid] = 0u;
-    double wv[D], hw[D], p0v[D], p1v[D];
+    double p0v[D], p1v[D];
     int kindv[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        wv[j] = phase_width(S, j, phase, k);
-        hw[j] = -0.5 * wv[j];
         p0v[j] = P.priors->p0[j];
         p1v[j] = P.priors->p1[j];
         kindv[j] = P.priors->kind[j];
     }
-    __syncthreads();
 
     const int wl = tid >> lgG;
     const int lane = tid & (G - 1);
@@ -245,12 +253,38 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
     const Like like(M);
     const double lstar = S->lstar;
     const uint32_t step = (uint32_t)S->step;
+    const int n_moves = (tuning ? 20 : P.iterations + P.burn_in) * D;
+    const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * D);
+    const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
+    const bool from_seed = phase == 0 || !tuning;  // else: continue from the previous tuning cycle
+    long long slot = 0;
+    uint32_t g = 0u;
+    double x[D], c[D];
+    double L = 0.0;
+    int base = -CH;                                // ring holds moves [base, base+CH)
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = c[j] = 0.0;
+
+    // state-independent per move: Philox block -> proposal variate r (or ndtri(r)) and acceptance
+    // uniform u.  Independent per move: the CH/G Philox chains of a lane overlap (ILP).
+    auto fill_ring = [&](int m0) {
+        base = m0;
+        __syncwarp(gmask);
+        for (int q = lane; q < CH; q += G) {
+            const int mv = base + q;
+            if (mv < n_moves) {
+                const U2 ru = philox_uniforms(P.seed, g, step, c2_base + (uint32_t)mv, GL_TAG_MOVE);
+                sb[q] = normal ? normcdfinv(ru.a) : ru.a;
+                ub[q] = ru.b;
+            }
+        }
+        __syncwarp(gmask);
+    };
 
     if (active) {
-        const long long slot = P.dead_list[w];
-        const uint32_t g = (uint32_t)(slot + P.row_offset);
-        double x[D], c[D];
-        if (phase == 0 || !tuning) {
+        slot = P.dead_list[w];
+        g = (uint32_t)(slot + P.row_offset);
+        if (from_seed) {
             long long pick = 0;
             if (lane == 0) {
                 for (uint32_t a = 0;; ++a) {       // survivor pick, redraw while dead
@@ -264,35 +298,34 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
             const double *src = P.live + pick * D;
 #pragma unroll
             for (int j = 0; j < D; ++j) x[j] = src[j];
-        } else {
+            L = like.template init_reg<D>(x, c);
+        }
+        fill_ring(0);
+    }
+    if (after_walk) { pdl_wait(); pdl_trigger(); }
+    __syncthreads();                               // acc_s cleared
+
+    double wv[D], hw[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        wv[j] = phase_width(S, j, phase, k);
+        hw[j] = -0.5 * wv[j];
+    }
+
+    if (active) {
+        if (!from_seed) {
             const double *src = P.scratch_x + (size_t)w * D;
 #pragma unroll
             for (int j = 0; j < D; ++j) x[j] = src[j];
+            L = like.template init_reg<D>(x, c);
         }
-        double L = like.template init_reg<D>(x, c);
         unsigned int accr[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) accr[j] = 0u;
 
-        const int n_moves = (tuning ? 20 : P.iterations + P.burn_in) * D;
-        const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * D);
-        const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
-        int m = 0, base = -CH;                     // ring holds moves [base, base+CH)
+        int m = 0;
         while (m < n_moves) {                      // group-uniform
-            if (m + G > base + CH) {
-                base = m;
-                __syncwarp(gmask);
-                for (int q = lane; q < CH; q += G) {
-                    const int mv = base + q;
-                    if (mv < n_moves) {
-                        const int jj = (int)((uint32_t)mv % (uint32_t)D);
-                        const U2 ru = philox_uniforms(P.seed, g, step, c2_base + (uint32_t)mv, GL_TAG_MOVE);
-                        sb[q] = __dmul_rn(normal ? normcdfinv(ru.a) : ru.a, reg_sel<D>(wv, jj));
-                        ub[q] = ru.b;
-                    }
-                }
-                __syncwarp(gmask);
-            }
+            if (m + G > base + CH) fill_ring(m);
             const int mine = m + lane;
             bool ok = false;
             double nj = 0.0, Lt = 0.0, cnew = 0.0;
@@ -301,7 +334,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
                 const double xj = reg_sel<D>(x, j);
                 // uniform: r*w + (x - w/2)   normal: ndtri(r)*w + x     (samplers.py:100,102)
                 const double loc = normal ? xj : __dadd_rn(xj, reg_sel<D>(hw, j));
-                nj = __dadd_rn(sb[mine - base], loc);
+                nj = __dadd_rn(__dmul_rn(sb[mine - base], reg_sel<D>(wv, j)), loc);
                 int kind = kindv[0];
 #pragma unroll
                 for (int i = 1; i < D; ++i) kind = j == i ? kindv[i] : kind;
@@ -386,10 +419,9 @@ struct WalkLauncher {
         int lgG = 0;
         while ((1 << lgG) < G) ++lgG;
         for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
-            if (G == 32) walk_reg_kernel<Like, D, true><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
-            else walk_reg_kernel<Like, D, false><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+            if (G == 32) GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, true>, dim3(blocks), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
+            else GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, false>, dim3(blocks), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
         }
-        GL_CHECK_LAUNCH();
         return GL_OK;
     }
     template <class Like>
