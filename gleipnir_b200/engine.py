@@ -171,7 +171,12 @@ class DeviceEngine(object):
         rows = int(st.n_rows)
         table = torch.empty((rows, self.d + 2), dtype=torch.float64, device=self.device)
         _lib.check(self.lib.gl_ns_export_dead(self._h, table.data_ptr(), self._stream()))
-        return table.cpu().numpy()
+        # pinned staging (torch's caching host allocator recycles the block between runs): the copy
+        # runs at PCIe rate instead of through a pageable bounce buffer
+        host = torch.empty((rows, self.d + 2), dtype=torch.float64, pin_memory=True)
+        host.copy_(table, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def dead_table(self):
         """Dead-point log as a host array [rows, d+2] (log_l, weight, x...) in death order,

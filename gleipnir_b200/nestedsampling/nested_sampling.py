@@ -66,7 +66,9 @@ class NestedSampling(NestedSamplingBase):
         self._n_iterations = 0
         self._n_evals = 0
         self._dead_points = list()
-        self._live_points = None
+        self._dead_values = None                    # host array [rows, d+2]; the DataFrame is built on first access
+        self._live_values = None
+        self._names = [sp.name for sp in sampled_parameters]
         self._post_eval = False
         self._posteriors = None
         self._engine = None
@@ -202,9 +204,12 @@ class NestedSampling(NestedSamplingBase):
         self._H = float(st.h_linear)
         self._logZ_err = float(np.sqrt(max(self._information, 0.0) / n))
         self._evidence_error = float(np.exp(self._logZ_err))
-        names = [sp.name for sp in self.sampled_parameters]
-        self._dead_points = pd.DataFrame(table_rows, columns=['log_l', 'weight'] + names)
-        self._live_points = pd.DataFrame(live, columns=names)
+        # the dead-point log is on the host now; wrapping it in a DataFrame (upstream's
+        # nested_sampling.py:211) costs milliseconds and is deferred to the first `dead_points` access
+        self._dead_values = np.ascontiguousarray(table_rows, dtype=np.float64)
+        self._live_values = live
+        self._dead_points = None
+        self._post_eval = False
         return self._log_evidence, self._logZ_err
 
     def _stopping_criterion(self):
@@ -253,7 +258,15 @@ class NestedSampling(NestedSamplingBase):
 
     @property
     def dead_points(self):
+        if self._dead_points is None and self._dead_values is not None:
+            self._dead_points = pd.DataFrame(self._dead_values, columns=['log_l', 'weight'] + self._names, copy=False)
         return self._dead_points
+
+    @property
+    def _live_points(self):
+        if self._live_values is None:
+            return None
+        return pd.DataFrame(self._live_values, columns=self._names)
 
     @dead_points.setter
     def dead_points(self, value):
@@ -261,8 +274,8 @@ class NestedSampling(NestedSamplingBase):
 
     # ---- post-processing (nested_sampling.py:266-336) ----------------------------------------
     def _normalised_weights(self):
-        logl = self._dead_points['log_l'].to_numpy()
-        w = self._dead_points['weight'].to_numpy()
+        logl = self._dead_values[:, 0]
+        w = self._dead_values[:, 1]
         with np.errstate(all="ignore"):
             nw = np.exp(np.log(w) + logl - self._log_evidence)     # = w*exp(logl)/Z without overflow
         return logl, np.where(np.isnan(nw), 0.0, nw)
@@ -273,28 +286,28 @@ class NestedSampling(NestedSamplingBase):
         assignment rule, deterministic sums); cached after the first call, as upstream."""
         if not self._post_eval:
             from ..posteriors import device_posteriors
-            vals = self._dead_points.to_numpy(dtype=np.float64)
+            vals = self._dead_values
             marg, edges, centers = device_posteriors(vals[:, 0], vals[:, 1], vals[:, 2:], self._log_evidence, nbins,
                                                      device=self.device)
             self._posteriors = dict()
-            for j, name in enumerate(self._dead_points.columns[2:]):
+            for j, name in enumerate(self._names):
                 self._posteriors[name] = (marg[j], edges[j], centers[j])
             self._post_eval = True
         return self._posteriors
 
     def max_loglikelihood(self):
-        return self._dead_points['log_l'].max()
+        return self._dead_values[:, 0].max()
 
     def deviance_ic(self):
         """DIC = p_D + D_bar with D = -2 logL averaged over the posterior weights."""
         logl, nw = self._normalised_weights()
         mask = nw > 0.0
-        params = self._dead_points[self._dead_points.columns[2:]].to_numpy()
+        params = self._dead_values[:, 2:]
         d_bar = np.average(-2.0 * logl[mask], weights=nw[mask])
         theta_bar = np.average(params[mask], weights=nw[mask], axis=0)
         p_d = d_bar - (-2.0 * self.loglikelihood(theta_bar))
         return p_d + d_bar
 
     def best_fit_likelihood(self):
-        vals = self._dead_points.to_numpy()
+        vals = self._dead_values
         return vals[int(np.argmax(vals[:, 0]))][2:]
