@@ -43,6 +43,8 @@ template <class Like, bool FULL>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkParams P, ModelDev M, int phase, int lgG) {
     extern __shared__ double sm[];
     EngineState *S = P.S;
+    pdl_wait();                                    // launched with launch_pdl (common.cuh): only the launch
+    pdl_trigger();                                 // latency of the next kernel overlaps this one
     if (!S->do_walk) return;                       // grid-uniform
     const int k = S->k_cur;
     const int d = P.d;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkParams P, ModelD
 // ---- register-resident walker for small d ------------------------------------------------------
 // The r01_g profile of walk_kernel at d = 2 shows a round of ~170 dependent, in-order-issued
 // instructions at ~8.6 cycles each, more than half of them shared-memory address arithmetic,
-// LDS/STS round trips of the walker state and runtime-d loop control.  For d <= REG_MAX_D the
+// LDS/STS round trips of the walker state and runtime-d loop control.  For d <= REG_MAX_D (8) the
 // point, the likelihood cache, widths and prior rows live in REGISTERS, replicated in every lane
 // of the group (commit = a shuffle from the accepting lane; no store, no group barrier), and d is
 // a template parameter.  Same moves, same arithmetic, same Philox counters: results are
@@ -434,6 +436,10 @@ struct WalkLauncher {
                     case 2: return launch_reg<Like, 2>(G);
                     case 3: return launch_reg<Like, 3>(G);
                     case 4: return launch_reg<Like, 4>(G);
+                    case 5: return launch_reg<Like, 5>(G);
+                    case 6: return launch_reg<Like, 6>(G);
+                    case 7: return launch_reg<Like, 7>(G);
+                    case 8: return launch_reg<Like, 8>(G);
                     default: break;
                 }
             }
@@ -455,10 +461,9 @@ struct WalkLauncher {
         int lgG = 0;
         while ((1 << lgG) < G) ++lgG;
         for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
-            if (G == 32) walk_kernel<Like, true><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
-            else walk_kernel<Like, false><<<blocks, WALK_THREADS, smem, st>>>(P, M, phase, lgG);
+            if (G == 32) GL_CUDA(launch_pdl(walk_kernel<Like, true>, dim3(blocks), dim3(WALK_THREADS), (size_t)smem, st, P, M, phase, lgG));
+            else GL_CUDA(launch_pdl(walk_kernel<Like, false>, dim3(blocks), dim3(WALK_THREADS), (size_t)smem, st, P, M, phase, lgG));
         }
-        GL_CHECK_LAUNCH();
         return GL_OK;
     }
 };

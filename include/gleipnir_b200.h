@@ -287,7 +287,7 @@ GL_API int gl_ns_force_multipass_select(gl_ns *ns, int32_t enable);
  * incrementally sorted live set (N <= 16384; measured slower than the radix select on one SM, kept
  * as a tested alternative), 4 cluster radix.
  * All paths produce identical results (tests compare them). */
-/* Walkers keep their state in registers when the model offers that form and d <= 4; this switch
+/* Walkers keep their state in registers when the model offers that form and d <= 8; this switch
  * forces the generic shared-memory walker (tests compare the two bit for bit). */
 GL_API int gl_ns_force_smem_walker(gl_ns *ns, int32_t enable);
 GL_API int gl_ns_set_select_path(gl_ns *ns, int32_t path);

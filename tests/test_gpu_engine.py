@@ -238,9 +238,10 @@ def test_reference_test_suite_flow(cuda):
 
 
 @pytest.mark.parametrize("kind,d,proposal", [("egg", 1, 0), ("egg", 2, 0), ("egg", 2, 1), ("egg", 3, 0), ("egg", 4, 1),
-                                             ("iid", 2, 0), ("iid", 3, 1), ("iid", 4, 0)])
+                                             ("iid", 2, 0), ("iid", 3, 1), ("iid", 4, 0), ("iid", 5, 0), ("egg", 6, 0),
+                                             ("iid", 7, 1), ("egg", 8, 0)])
 def test_register_and_shared_memory_walkers_are_bit_identical(cuda, kind, d, proposal):
-    """d <= 4: the walker keeps its state in registers (walk_reg_kernel); it must retire exactly the
+    """d <= 8: the walker keeps its state in registers (walk_reg_kernel); it must retire exactly the
     chain of the generic shared-memory walker -- mixed prior families, both proposal kinds, several
     group sizes."""
     like, _ = _mk(kind, d)
@@ -248,7 +249,7 @@ def test_register_and_shared_memory_walkers_are_bit_identical(cuda, kind, d, pro
         table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
     else:
         rows = [(pr.GL_PRIOR_NORM, 0.0, 3.0), (pr.GL_PRIOR_UNIFORM, -5.0, 10.0), (pr.GL_PRIOR_LOGUNIFORM, 0.01, 5.0),
-                (pr.GL_PRIOR_NORM, 0.5, 2.0)]
+                (pr.GL_PRIOR_NORM, 0.5, 2.0)] * 2
         table = rows[:d]
     N, k, n_deaths = 300, 30, 600
     ref = None
