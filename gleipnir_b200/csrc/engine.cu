@@ -1453,6 +1453,94 @@ __global__ void __launch_bounds__(EXPORT_THREADS) export_batches_kernel(
     }
 }
 
+// Sharded run: every rank's log, all-gathered as packed rows [world][mx][d+4] = (logL, weight, x[d],
+// global slot, step) with counts[r] valid rows in rank r's block (dead rows in step order, then the
+// survivors with step -1), assembled into ONE table in death order: CTA s merges the segments of
+// step s from all ranks and sorts them by (key, slot); CTAs n_steps.. copy the survivors rank by
+// rank (= global slot order).  Every batch but the last holds exactly batch_k rows.
+__device__ __forceinline__ long long packed_step_lower_bound(const double *__restrict__ rows, long long n, int w,
+                                                             int d, int step) {
+    long long a = 0, b = n;                        // first row whose step (survivors: +inf) is >= `step`
+    while (a < b) {
+        const long long m = (a + b) >> 1;
+        const int sm = (int)rows[m * w + d + 3];
+        if ((sm < 0 ? 0x7fffffff : sm) < step) a = m + 1; else b = m;
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(EXPORT_THREADS) export_gathered_kernel(
+    const double *__restrict__ packed, const long long *__restrict__ counts, int world, long long mx, int d, int batch_k,
+    int n_steps, long long n_dead_total, int seg_cap, double *__restrict__ out) {
+    extern __shared__ unsigned long long sk[];                 // keys[seg_cap] | tags[seg_cap] | src[seg_cap] (u32)
+    unsigned long long *sr = sk + seg_cap;
+    unsigned int *ssrc = reinterpret_cast<unsigned int *>(sr + seg_cap);
+    __shared__ long long s_lo[64], s_n[64];
+    const int w = d + 4;
+    if ((int)blockIdx.x < n_steps) {
+        const int step = blockIdx.x;
+        if (threadIdx.x < world) {
+            const double *rows = packed + (long long)threadIdx.x * mx * w;
+            const long long lo = packed_step_lower_bound(rows, counts[threadIdx.x], w, d, step);
+            const long long hi = packed_step_lower_bound(rows, counts[threadIdx.x], w, d, step + 1);
+            s_lo[threadIdx.x] = lo;
+            s_n[threadIdx.x] = hi - lo;
+        }
+        __syncthreads();
+        int n = 0;
+        for (int r = 0; r < world; ++r) n += (int)s_n[r];
+        if (n <= 0 || n > seg_cap) return;          // (host checks batch_k <= seg_cap)
+        for (int i = threadIdx.x; i < seg_cap; i += EXPORT_THREADS) { sk[i] = ~0ull; sr[i] = ~0ull; }
+        __syncthreads();
+        int off = 0;
+        for (int r = 0; r < world; ++r) {
+            const int nr = (int)s_n[r];
+            const long long row0 = (long long)r * mx + s_lo[r];
+            for (int i = threadIdx.x; i < nr; i += EXPORT_THREADS) {
+                const double *row = packed + (row0 + i) * w;
+                sk[off + i] = sort_key(row[0]);
+                sr[off + i] = (unsigned long long)(long long)row[d + 2] << 24 | (unsigned long long)(off + i);
+                ssrc[off + i] = (unsigned int)(row0 + i);
+            }
+            off += nr;
+        }
+        __syncthreads();
+        for (int size = 2; size <= seg_cap; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < seg_cap / 2; t += EXPORT_THREADS) {
+                    const int i = 2 * t - (t & (stride - 1));
+                    const int j = i + stride;
+                    const bool up = (i & size) == 0;
+                    const unsigned long long ki = sk[i], kj = sk[j], ri = sr[i], rj = sr[j];
+                    const bool gt = ki > kj || (ki == kj && ri > rj);
+                    if (gt == up) { sk[i] = kj; sk[j] = ki; sr[i] = rj; sr[j] = ri; }
+                }
+                __syncthreads();
+            }
+        }
+        const long long out0 = (long long)step * batch_k;
+        for (long long e = threadIdx.x; e < (long long)n * (d + 2); e += EXPORT_THREADS) {
+            const int q = (int)(e / (d + 2)), c = (int)(e - (long long)q * (d + 2));
+            const long long src = ssrc[sr[q] & 0xffffffull];
+            out[(out0 + q) * (d + 2) + c] = packed[src * w + c];
+        }
+    } else {
+        const int r = (int)blockIdx.x - n_steps;    // survivors of rank r
+        long long out0 = n_dead_total;
+        for (int q = 0; q < r; ++q) {
+            const long long nd = packed_step_lower_bound(packed + (long long)q * mx * w, counts[q], w, d, 0x7fffffff);
+            out0 += counts[q] - nd;
+        }
+        const long long nd = packed_step_lower_bound(packed + (long long)r * mx * w, counts[r], w, d, 0x7fffffff);
+        const long long ns = counts[r] - nd;
+        for (long long e = threadIdx.x; e < ns * (d + 2); e += EXPORT_THREADS) {
+            const long long q = e / (d + 2);
+            const int c = (int)(e - q * (d + 2));
+            out[(out0 + q) * (d + 2) + c] = packed[((long long)r * mx + nd + q) * w + c];
+        }
+    }
+}
+
 }  // namespace gl
 
 // ============================== host side / C ABI ==========================================
@@ -1934,6 +2022,24 @@ int gl_ns_export_dead(gl_ns *ns, double *table_dev, void *stream) {
         ns->buf.dead_step, ns->d, seg, table_dev);
     GL_CHECK_LAUNCH();
     ns->h_launches += 1;
+    return GL_OK;
+}
+
+int gl_export_gathered_table(const double *packed_dev, const int64_t *counts_dev, int32_t world, int64_t max_rows,
+                             int32_t d, int32_t batch_k, int32_t n_steps, int64_t n_dead_total, double *table_dev,
+                             void *stream) {
+    GL_REQUIRE(packed_dev != nullptr && counts_dev != nullptr && table_dev != nullptr, "NULL argument");
+    GL_REQUIRE(world >= 1 && world <= 64 && d >= 1 && batch_k >= 1 && n_steps >= 0, "bad argument");
+    GL_REQUIRE(batch_k <= 8192, "batch_k=%d > 8192: order such tables on the host", batch_k);
+    GL_REQUIRE((long long)world * max_rows < (1LL << 32), "gathered log too large");
+    int seg = 2;
+    while (seg < batch_k) seg <<= 1;
+    const int smem = seg * 20;
+    int rc = gl::ensure_smem((const void *)gl::export_gathered_kernel, smem);
+    if (rc) return rc;
+    gl::export_gathered_kernel<<<n_steps + world, gl::EXPORT_THREADS, smem, (cudaStream_t)stream>>>(
+        packed_dev, (const long long *)counts_dev, world, max_rows, d, batch_k, n_steps, n_dead_total, seg, table_dev);
+    GL_CHECK_LAUNCH();
     return GL_OK;
 }
 

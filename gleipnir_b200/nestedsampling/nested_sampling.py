@@ -107,7 +107,8 @@ class NestedSampling(NestedSamplingBase):
     def _run_sharded(self, dist, loglike, table, n, k, seed, scfg, n_deaths, verbose):
         """One shard per rank, global threshold by all-gather (gleipnir_b200/sharded.py)."""
         import torch
-        from ..sharded import gather_dead_tables, get_nccl_comm, run_sharded_native, shard_bounds
+        from ..sharded import (gather_dead_table_device, gather_dead_tables, get_nccl_comm, run_sharded_native,
+                               shard_bounds)
         comm = get_nccl_comm()
         rank = comm.rank
         seed_t = torch.tensor([seed], dtype=torch.int64, device="cuda")
@@ -120,14 +121,17 @@ class NestedSampling(NestedSamplingBase):
         self._engine = eng
         run_sharded_native(eng, comm, n_deaths, k)
         st = eng.state()
-        rows, idx, step = gather_dead_tables(eng)
-        from ..engine import death_order
-        order = death_order(rows[:, 0], idx, step)
+        if k <= 8192:
+            table_rows = gather_dead_table_device(eng, k, n_deaths)     # ordered on the device
+        else:
+            rows, idx, step = gather_dead_tables(eng)
+            from ..engine import death_order
+            table_rows = rows[death_order(rows[:, 0], idx, step)]
         evals = torch.tensor([st.n_evals], dtype=torch.int64, device="cuda")
         dist.all_reduce(evals)
         live = torch.empty((n, eng.d), dtype=torch.float64, device=eng.device)
         dist.all_gather_into_tensor(live, eng.live)
-        return st, rows[order], int(evals.item()), live.cpu().numpy()
+        return st, table_rows, int(evals.item()), live.cpu().numpy()
 
     def run(self, verbose=False):
         loglike = require_device_loglikelihood(self.loglikelihood)

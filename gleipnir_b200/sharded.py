@@ -180,6 +180,40 @@ def gather_dead_tables(engine, group=None):
     return cat[:, :d + 2], cat[:, d + 2].astype(np.int64), cat[:, d + 3].astype(np.int64)
 
 
+def gather_dead_table_device(engine, batch_k, n_deaths, group=None):
+    """All ranks' dead-point logs assembled on the device into the reference's table (death order):
+    one padded all-gather over NCCL, one kernel (gl_export_gathered_table), one pinned D2H copy.
+    Returns the host array [rows, d+2]; every rank gets the same table.  batch_k <= 8192."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    world = dist.get_world_size(group)
+    rows = int(engine.state().n_rows)
+    d = engine.d
+    dev = engine.device
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([rows], dtype=torch.int64, device=dev), group=group)
+    counts_h = counts.cpu()
+    mx, total = int(counts_h.max()), int(counts_h.sum())
+    mine = torch.empty((mx, d + 4), dtype=torch.float64, device=dev)
+    mine[:rows, 0] = engine.dead_logl[:rows]
+    mine[:rows, 1] = engine.dead_w[:rows]
+    mine[:rows, 2:2 + d] = engine.dead_x[:rows]
+    mine[:rows, 2 + d] = engine.dead_idx[:rows].to(torch.float64)        # exact below 2^53
+    mine[:rows, 3 + d] = engine.dead_step[:rows].to(torch.float64)
+    allr = torch.empty((world * mx, d + 4), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allr, mine, group=group)
+    n_steps = (int(n_deaths) + int(batch_k) - 1) // int(batch_k)
+    table = torch.empty((total, d + 2), dtype=torch.float64, device=dev)
+    _lib.check(engine.lib.gl_export_gathered_table(allr.data_ptr(), counts.data_ptr(), world, mx, d, int(batch_k), n_steps,
+                                                   int(n_deaths), table.data_ptr(), engine._stream()))
+    host = torch.empty((total, d + 2), dtype=torch.float64, pin_memory=True)
+    host.copy_(table, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host.numpy()
+
+
 def run_sharded_native(engine, nccl_comm, n_deaths, batch_k, candidate_sigmas=DEFAULT_CANDIDATE_SIGMAS,
                        check_overflow=True):
     """Whole sharded run enqueued from C++ (gl_ns_advance_sharded / gl_ns_finalize_sharded).

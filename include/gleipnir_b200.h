@@ -261,6 +261,15 @@ GL_API int gl_ns_shard_final_partial(gl_ns *ns, double *partial_dev, void *strea
 GL_API int gl_ns_shard_finalize(gl_ns *ns, const double *gathered_partials_dev, int32_t world, int32_t rank,
                                 void *stream);
 
+/* Sharded run, table assembly on the device: `packed_dev` = the ranks' logs all-gathered as rows
+ * [world][max_rows][d+4] = (log_l, weight, x[d], global slot, step; survivors carry step -1 and
+ * come last in a rank's block), `counts_dev[world]` valid rows per rank.  Writes the
+ * [sum(counts), d+2] table in death order (nested_sampling.py:130-133,195-203,211): batches in
+ * sequence, ascending (log_l, slot) inside a batch, survivors last in global slot order. */
+GL_API int gl_export_gathered_table(const double *packed_dev, const int64_t *counts_dev, int32_t world,
+                                    int64_t max_rows, int32_t d, int32_t batch_k, int32_t n_steps,
+                                    int64_t n_dead_total, double *table_dev, void *stream);
+
 /* Native sharded loop: NCCL all-gathers enqueued on the engine's stream from C++ (libnccl is
  * dlopen'ed on first use).  gl_comm_unique_id on rank 0 -> broadcast the bytes by any means
  * (torch.distributed in the Python host) -> gl_comm_create on every rank (collective). */

@@ -174,3 +174,47 @@ def test_truncated_exchange_overflow_is_detected_and_repeated(cuda, multipass):
         ta, tb = a.dead_table(), b.dead_table()
         assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
         assert a.state().log_z == b.state().log_z and not a.overflowed()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gathered_table_assembled_on_the_device_matches_host_ordering(cuda, world):
+    """gl_export_gathered_table (sharded run(): one kernel instead of a host lexsort) against
+    engine.death_order applied to the same gathered rows."""
+    import torch
+    from gleipnir_b200 import _lib
+    from gleipnir_b200 import likelihoods as lk
+    from gleipnir_b200.engine import DeviceEngine, death_order
+    n, k, deaths = 2000, 300, 2000           # short last batch (2000 = 6*300 + 200)
+    table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * 2
+    dev = []
+    for r in range(world):
+        off, n_loc = shard_bounds(n, world, r)
+        dev.append(DeviceEngine(table, lk.EggCartonLogLikelihood(2), n_loc, k, deaths, seed=3, row_offset=off,
+                                global_population=n, iterations=3, tuning_cycles=1))
+    run_sharded(dev, LocalComm(world), deaths, k)
+    d = 2
+    counts = [int(e.state().n_rows) for e in dev]
+    mx = max(counts)
+    packed = torch.zeros((world, mx, d + 4), dtype=torch.float64, device=dev[0].device)
+    for r, e in enumerate(dev):
+        c = counts[r]
+        packed[r, :c, 0] = e.dead_logl[:c]
+        packed[r, :c, 1] = e.dead_w[:c]
+        packed[r, :c, 2:2 + d] = e.dead_x[:c]
+        packed[r, :c, 2 + d] = e.dead_idx[:c].to(torch.float64)
+        packed[r, :c, 3 + d] = e.dead_step[:c].to(torch.float64)
+    total = sum(counts)
+    out = torch.full((total, d + 2), float("nan"), dtype=torch.float64, device=dev[0].device)
+    cnt = torch.tensor(counts, dtype=torch.int64, device=dev[0].device)
+    n_steps = (deaths + k - 1) // k
+    lib = _lib.load()
+    _lib.check(lib.gl_export_gathered_table(packed.data_ptr(), cnt.data_ptr(), world, mx, d, k, n_steps, deaths,
+                                            out.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    rows = np.concatenate([packed[r, :counts[r]].cpu().numpy() for r in range(world)])
+    order = death_order(rows[:, 0], rows[:, d + 2].astype(np.int64), rows[:, d + 3].astype(np.int64))
+    want = rows[order][:, :d + 2]
+    assert total == deaths + (n - 200)
+    assert np.array_equal(got, want)
+    assert abs(got[:, 1].sum() - 1.0) < 1e-12
