@@ -965,7 +965,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     long long row_offset, double n_global, long long capacity, const double *__restrict__ live,
     const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
     double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
-    long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    long long *__restrict__ dead_idx, int *__restrict__ dead_step,
+    int defer_book /* a batch that will be refilled leaves record + accumulate to the first walker launch */) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
@@ -1017,10 +1018,35 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     // (the first cluster barrier inside also orders every is_dead clear above before the new flags)
     const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, N, k, dead_list, is_dead);
 
-    // ---- record: rows spread over the cluster --------------------------------------------------------
     const double logw = logX0 - log(n_global + 1.0);
     const double w = exp(logw);
     const bool room = base_row + k <= capacity;
+    if (defer_book && n_dead0 + k < n_target) {
+        // the walkers only need dead_list / is_dead / L* / the batch header: publish those and leave
+        // the dead-row copy and the evidence sums to the first walker launch (walk_reg_kernel, phase 0),
+        // where they run beside the walkers instead of in front of them
+        if (c == 0 && tid == 0) {
+            S->book_logw = logw;
+            S->book_w = w;
+            S->book_base_row = base_row;
+            S->book_step = step_now;
+            S->book_room = room ? 1 : 0;
+            S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
+            S->n_dead = n_dead0 + k;
+            if (room) S->n_rows = base_row + k;
+            S->lstar = key_to_double(kstar);
+            S->k_cur = k;
+            S->do_walk = 1;
+            if (end_walk_tc >= 0) {
+                S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
+                S->step = step_now;
+            }
+        }
+        cluster.sync();
+        return;
+    }
+
+    // ---- record: rows spread over the cluster --------------------------------------------------------
     if (room) {
         for (int e = c * KC_THREADS + tid; e < k * d; e += KC_CTAS * KC_THREADS) {
             const int q = e / d, j = e - q * d;
@@ -1575,6 +1601,7 @@ struct gl_ns {
     bool defer_ok;                                // inside gl_ns_advance(_sharded): the next op is a kill / candidates
     bool sharded_loop;                            // inside gl_ns_advance_sharded
     bool force_smem_walker;                       // tests: generic shared-memory walker even for small d
+    bool book_deferred;                           // the last kill left record + accumulate to the next refill
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -1650,6 +1677,13 @@ static WalkParams walk_params(const gl_ns *ns) {
     P.k_max = ns->cfg.batch_k;
     P.lanes = ns->cfg.walker_lanes;
     P.force_smem_state = ns->force_smem_walker ? 1 : 0;
+    P.book = ns->book_deferred ? 1 : 0;
+    P.n_global = (double)ns->cfg.global_population;
+    P.dead_x = ns->buf.dead_x;
+    P.dead_logl = ns->buf.dead_logl;
+    P.dead_w = ns->buf.dead_w;
+    P.dead_idx = (long long *)ns->buf.dead_idx;
+    P.dead_step = ns->buf.dead_step;
     return P;
 }
 
@@ -1728,13 +1762,21 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
                 ns->si0, ns->si1, n2);
             ns->h_sorted_ready = true;
         } else if (use_cluster) {
+            // inside gl_ns_advance a batch that will be refilled by the register walker (>= 1 tuning launch
+            // in front of the production launch that overwrites the dead slots) defers its bookkeeping
+            const bool defer_book = ns->defer_ok && !ns->sharded_loop && ns->cfg.tuning_cycles >= 1 &&
+                                    !ns->force_smem_walker && ns->d <= model_reg_max_d(ns->model.kind);
             const int smem = (int)(sizeof(unsigned long long) * ((N + KC_CTAS - 1) / KC_CTAS));
             int rc0 = ensure_smem((const void *)kill_cluster_kernel, smem);
             if (rc0) return rc0;
             GL_CUDA(launch_pdl(kill_cluster_kernel, dim3(KC_CTAS), dim3(KC_THREADS), (size_t)smem, st, ns->S, tc_arg, epw,
                                k_req, n_target, (int)N, ns->d, ns->cfg.row_offset, n_global, ns->cfg.dead_capacity,
                                ns->buf.live, ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl,
-                               ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step));
+                               ns->buf.dead_w, (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0));
+            long long kh = n_target - ns->h_n_dead;
+            if (kh > k_req) kh = k_req;
+            if (kh > N - 1) kh = N - 1;
+            ns->book_deferred = defer_book && kh > 0 && ns->h_n_dead + kh < n_target;
         } else {
             const int smem = (int)(sizeof(unsigned long long) * N);
             int rc0 = ensure_smem((const void *)kill_small_kernel<false>, smem);
@@ -1790,6 +1832,7 @@ static int end_walk_launch(gl_ns *ns, cudaStream_t st, long long evals_per_walke
 static int refill_launch(gl_ns *ns, cudaStream_t st) {
     prof_mark(ns, ns->ev_walk, st);
     int rc = walk_launch(walk_params(ns), ns->model, st);
+    ns->book_deferred = false;
     if (rc) return rc;
     prof_mark(ns, ns->ev_walk, st);
     ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
@@ -1865,6 +1908,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->defer_ok = false;
     ns->sharded_loop = false;
     ns->force_smem_walker = false;
+    ns->book_deferred = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;

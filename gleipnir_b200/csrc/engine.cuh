@@ -32,6 +32,10 @@ struct EngineState {                 // one instance in device memory per engine
     int sort_cur;                    // which of the two buffers is current
     int front_dead;                  // leading entries of the current buffer that were killed (now stale)
     int shard_overflow;              // sticky: a truncated candidate exchange could not prove its selection exact
+    // bookkeeping of the current batch left to the first walker launch (kill_cluster_kernel, defer_book)
+    double book_logw, book_w;        // ln weight / weight of every death of the batch
+    long long book_base_row;         // first row of the batch in the dead log
+    int book_step, book_room;        // batch id; the rows fit in the log
 };
 
 struct WalkParams {                  // by-value kernel parameter
@@ -49,6 +53,12 @@ struct WalkParams {                  // by-value kernel parameter
     int d, iterations, burn_in, tuning_cycles, proposal, k_max;
     int lanes;                       // lanes per walker (0 = choose from k_max)
     int force_smem_state;            // tests: use the generic shared-memory walker even for small d
+    // deferred bookkeeping (walk_reg_kernel, phase 0): dead-row record by the walkers, evidence update by one extra block
+    int book;
+    double n_global;
+    double *dead_x, *dead_logl, *dead_w;
+    long long *dead_idx;
+    int *dead_step;
 };
 
 // walker.cu

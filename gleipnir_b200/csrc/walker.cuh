@@ -208,6 +208,81 @@ __device__ __forceinline__ double reg_sel(const double (&a)[D], int j) {
     return r;
 }
 
+// ---- deferred bookkeeping of a batch (see kill_cluster_kernel, defer_book) -----------------------
+// One extra 128-thread block of the first walker launch does the evidence / information update of
+// the batch the walkers are refilling.  It reproduces the summation tree of the 1024-thread kernels
+// (accumulate_kernel, kill_small_kernel) with 8 virtual threads per thread, so the run stays
+// bit-identical to every other path.
+template <bool MAX>
+__device__ __forceinline__ double block_reduce_v8(const double (&a)[8], double *scr) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const double t = MAX ? warp_max(a[v]) : warp_sum(a[v]);
+        if (lane == 0) scr[4 * v + wid] = t;       // virtual warp of virtual thread tid + 128 v
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double t = scr[lane];
+        t = MAX ? warp_max(t) : warp_sum(t);
+        if (lane == 0) scr[32] = t;
+    }
+    __syncthreads();
+    return scr[32];
+}
+
+__device__ inline void book_accumulate_block(EngineState *S, const WalkParams &P) {
+    static_assert(WALK_THREADS == 128, "8 virtual threads per thread emulate a 1024-thread block");
+    __shared__ double scr[33];
+    const int tid = threadIdx.x;
+    const int k = S->k_cur;
+    const double logw = S->book_logw, w = S->book_w, m_old = S->M;
+    double a[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        a[v] = -INFINITY;
+        for (int i = tid + WALK_THREADS * v; i < k; i += 1024) {
+            const double lw = logw + P.logl[P.dead_list[i]];
+            if (isfinite(lw)) a[v] = fmax(a[v], lw);
+        }
+    }
+    const double mx = block_reduce_v8<true>(a, scr);
+    const double m_new = fmax(m_old, mx);
+    double sz[8], sh[8], zl[8], hl[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        sz[v] = sh[v] = zl[v] = hl[v] = 0.0;
+        for (int i = tid + WALK_THREADS * v; i < k; i += 1024) {
+            const double L = P.logl[P.dead_list[i]];
+            const double lw = logw + L;
+            if (isfinite(lw)) {
+                const double t = exp(lw - m_new);
+                sz[v] += t;
+                sh[v] += t * L;
+            }
+            const double dZ = w * exp(L);
+            zl[v] += dZ;
+            const double dH = dZ * L;
+            if (dH == dH) hl[v] += dH;
+        }
+    }
+    const double szs = block_reduce_v8<false>(sz, scr);
+    const double shs = block_reduce_v8<false>(sh, scr);
+    const double zls = block_reduce_v8<false>(zl, scr);
+    const double hls = block_reduce_v8<false>(hl, scr);
+    if (tid == 0) {
+        if (mx > -INFINITY) {
+            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+            S->Zs = S->Zs * scale + szs;
+            S->Hs = S->Hs * scale + shs;
+            S->M = m_new;
+        }
+        S->Z_lin += zls;
+        S->H_lin += hls;
+    }
+}
+
 template <class Like, int D, bool FULL>
 __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, ModelDev M, int phase, int lgG) {
     extern __shared__ double sm[];                 // r[WPB][CH] | u[WPB][CH]: raw Philox uniforms of the ring
@@ -221,6 +296,11 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
     // overlaps the tail of that launch.
     const bool after_walk = phase > 0;
     if (!after_walk) { pdl_wait(); pdl_trigger(); }
+    const bool book = phase == 0 && P.book != 0;   // this launch also does the batch's deferred bookkeeping
+    if (book && blockIdx.x == gridDim.x - 1) {     // (one extra block; the host only asks when do_walk is certain)
+        book_accumulate_block(S, P);
+        return;
+    }
     const bool do_walk = S->do_walk != 0;          // grid-uniform
     const int k = S->k_cur;
     const int G = FULL ? 32 : (1 << lgG);
@@ -286,6 +366,16 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
     if (active) {
         slot = P.dead_list[w];
         g = (uint32_t)(slot + P.row_offset);
+        if (book && S->book_room) {                // record_kernel's job: each walker logs the row it replaces
+            const long long row = S->book_base_row + w;
+            for (int j = lane; j < D; j += G) P.dead_x[row * D + j] = P.live[slot * D + j];
+            if (lane == 0) {
+                P.dead_logl[row] = P.logl[slot];
+                P.dead_w[row] = S->book_w;
+                P.dead_idx[row] = slot + P.row_offset;
+                P.dead_step[row] = S->book_step;
+            }
+        }
         if (from_seed) {
             long long pick = 0;
             if (lane == 0) {
@@ -421,8 +511,9 @@ struct WalkLauncher {
         int lgG = 0;
         while ((1 << lgG) < G) ++lgG;
         for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
-            if (G == 32) GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, true>, dim3(blocks), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
-            else GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, false>, dim3(blocks), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
+            const int nb = blocks + (phase == 0 && P.book ? 1 : 0);        // + the bookkeeping block
+            if (G == 32) GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, true>, dim3(nb), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
+            else GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, false>, dim3(nb), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
         }
         return GL_OK;
     }
