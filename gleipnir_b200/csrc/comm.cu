@@ -97,6 +97,7 @@ extern "C" int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_lo
 extern "C" int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas);
 extern "C" int64_t gl_ns_local_population(const gl_ns *ns);
 extern "C" void gl_ns_internal_sharded_loop(gl_ns *ns, int on);
+extern "C" void gl_ns_internal_commit_refills(gl_ns *ns, int yes);
 
 extern "C" {
 
@@ -177,6 +178,7 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
         if (rc) return rc;
         rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)m, st);
         if (rc) return rc;
+        gl_ns_internal_commit_refills(ns, done + k < n_deaths_total ? 1 : 0);
         rc = gl_ns_shard_commit_truncated(ns, c->recv, c->world, c->rank, k, m, c->keys, stream);
         if (rc) return rc;
         done += k;

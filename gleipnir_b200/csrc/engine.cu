@@ -1135,7 +1135,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     double n_global, long long capacity, const long long *__restrict__ cand_list, long long *__restrict__ positions,
     const double *__restrict__ live, const double *__restrict__ logl, long long *__restrict__ dead_list,
     unsigned char *__restrict__ is_dead, double *__restrict__ dead_x, double *__restrict__ dead_logl,
-    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step) {
+    double *__restrict__ dead_w, long long *__restrict__ dead_idx, int *__restrict__ dead_step,
+    int defer_book /* record + accumulate are left to the first walker launch of the refill that follows */) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
@@ -1167,6 +1168,28 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     const double logw = logX0 - log(n_global + 1.0);
     const double w = exp(logw);
     const bool room = base_row + n_own <= capacity;
+    if (defer_book) {
+        for (int i = c * KC_THREADS + tid; i < n_own; i += KC_CTAS * KC_THREADS) {
+            const long long slot = cand_list[positions[start + i] - (long long)rank * m];
+            dead_list[i] = slot;
+            is_dead[slot] = 1;
+        }
+        if (c == 0 && tid == 0) {
+            S->book_logw = logw;
+            S->book_w = w;
+            S->book_base_row = base_row;
+            S->book_step = step_now;
+            S->book_room = room ? 1 : 0;
+            S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
+            S->n_dead = n_dead0 + k;
+            if (room) S->n_rows = base_row + n_own;
+            S->lstar = key_to_double(kstar);
+            S->k_cur = n_own;
+            S->do_walk = 1;
+        }
+        cluster.sync();
+        return;
+    }
     for (int i = c * KC_THREADS + tid; i < n_own; i += KC_CTAS * KC_THREADS) {
         const long long slot = cand_list[positions[start + i] - (long long)rank * m];
         dead_list[i] = slot;
@@ -1600,8 +1623,12 @@ struct gl_ns {
     bool end_walk_deferred;                       // last refill's epilogue is still to run
     bool defer_ok;                                // inside gl_ns_advance(_sharded): the next op is a kill / candidates
     bool sharded_loop;                            // inside gl_ns_advance_sharded
+    bool commit_refills;                          // ... and the next commit is followed by a refill
     bool force_smem_walker;                       // tests: generic shared-memory walker even for small d
-    bool book_deferred;                           // the last kill left record + accumulate to the next refill
+    bool book_deferred;                           // the last kill / commit left record + accumulate to the next refill
+    int book_k;                                   // values of that batch: L(i) = book_vals[book_idx[i]]
+    const double *book_vals;
+    const long long *book_idx;
     std::vector<cudaEvent_t> ev_walk, ev_sel;     // (start, stop) pairs on the launching stream
     long long prof_walk_launches, prof_sel_launches;
 };
@@ -1677,7 +1704,9 @@ static WalkParams walk_params(const gl_ns *ns) {
     P.k_max = ns->cfg.batch_k;
     P.lanes = ns->cfg.walker_lanes;
     P.force_smem_state = ns->force_smem_walker ? 1 : 0;
-    P.book = ns->book_deferred ? 1 : 0;
+    P.book = ns->book_deferred ? ns->book_k : 0;
+    P.book_vals = ns->book_vals;
+    P.book_idx = ns->book_idx;
     P.n_global = (double)ns->cfg.global_population;
     P.dead_x = ns->buf.dead_x;
     P.dead_logl = ns->buf.dead_logl;
@@ -1777,6 +1806,9 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
             if (kh > k_req) kh = k_req;
             if (kh > N - 1) kh = N - 1;
             ns->book_deferred = defer_book && kh > 0 && ns->h_n_dead + kh < n_target;
+            ns->book_k = (int)kh;
+            ns->book_vals = ns->buf.logl;
+            ns->book_idx = ns->dead_list;
         } else {
             const int smem = (int)(sizeof(unsigned long long) * N);
             int rc0 = ensure_smem((const void *)kill_small_kernel<false>, smem);
@@ -1907,6 +1939,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->end_walk_deferred = false;
     ns->defer_ok = false;
     ns->sharded_loop = false;
+    ns->commit_refills = false;
     ns->force_smem_walker = false;
     ns->book_deferred = false;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
@@ -2182,7 +2215,10 @@ int64_t gl_ns_local_population(const gl_ns *ns) { return ns ? ns->cfg.population
 void gl_ns_internal_sharded_loop(gl_ns *ns, int on) {
     ns->sharded_loop = on != 0;
     ns->defer_ok = on != 0;
+    ns->commit_refills = false;
 }
+// ... and whether the commit it is about to issue will be followed by a refill
+void gl_ns_internal_commit_refills(gl_ns *ns, int yes) { ns->commit_refills = yes != 0; }
 
 int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t n_local, double sigmas) {
     if (k < 1 || world < 1 || n_local < 2) return 0;
@@ -2211,12 +2247,19 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
         const int smem = (int)(8 * (((long long)world * m + gl::KC_CTAS - 1) / gl::KC_CTAS));
         int rc0 = gl::ensure_smem((const void *)gl::shard_commit_cluster_kernel, smem);
         if (rc0) return rc0;
+        // native loop, and a refill by the register walker follows this commit: it does the bookkeeping
+        const bool defer_book = ns->sharded_loop && ns->commit_refills && ns->cfg.tuning_cycles >= 1 &&
+                                !ns->force_smem_walker && ns->d <= gl::model_reg_max_d(ns->model.kind);
         gl::prof_mark(ns, ns->ev_sel, st);
         GL_CUDA(gl::launch_pdl(gl::shard_commit_cluster_kernel, dim3(gl::KC_CTAS), dim3(gl::KC_THREADS), (size_t)smem, st,
                                ns->S, gathered_logl_dev, world, rank, k, m, ns->d, ns->cfg.row_offset, n_global,
                                ns->cfg.dead_capacity, ns->cand_list, ns->positions, ns->buf.live, ns->buf.logl,
                                ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w,
-                               (long long *)ns->buf.dead_idx, ns->buf.dead_step));
+                               (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0));
+        ns->book_deferred = defer_book;
+        ns->book_k = k;
+        ns->book_vals = gathered_logl_dev;
+        ns->book_idx = ns->positions;
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;

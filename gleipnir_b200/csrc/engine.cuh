@@ -36,6 +36,8 @@ struct EngineState {                 // one instance in device memory per engine
     double book_logw, book_w;        // ln weight / weight of every death of the batch
     long long book_base_row;         // first row of the batch in the dead log
     int book_step, book_room;        // batch id; the rows fit in the log
+    double book_part[4][32];         // per-virtual-warp partial sums of the book blocks
+    unsigned int book_count;         // book blocks finished (last one combines and resets)
 };
 
 struct WalkParams {                  // by-value kernel parameter
@@ -54,7 +56,9 @@ struct WalkParams {                  // by-value kernel parameter
     int lanes;                       // lanes per walker (0 = choose from k_max)
     int force_smem_state;            // tests: use the generic shared-memory walker even for small d
     // deferred bookkeeping (walk_reg_kernel, phase 0): dead-row record by the walkers, evidence update by one extra block
-    int book;
+    int book;                        // 0, or the number of values of the batch (global k)
+    const double *book_vals;         // L(i) = book_vals[book_idx[i]], i < book: logl/dead_list, or gathered/positions
+    const long long *book_idx;
     double n_global;
     double *dead_x, *dead_logl, *dead_w;
     long long *dead_idx;

@@ -208,78 +208,78 @@ __device__ __forceinline__ double reg_sel(const double (&a)[D], int j) {
     return r;
 }
 
-// ---- deferred bookkeeping of a batch (see kill_cluster_kernel, defer_book) -----------------------
-// One extra 128-thread block of the first walker launch does the evidence / information update of
-// the batch the walkers are refilling.  It reproduces the summation tree of the 1024-thread kernels
-// (accumulate_kernel, kill_small_kernel) with 8 virtual threads per thread, so the run stays
-// bit-identical to every other path.
-template <bool MAX>
-__device__ __forceinline__ double block_reduce_v8(const double (&a)[8], double *scr) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __syncthreads();
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        const double t = MAX ? warp_max(a[v]) : warp_sum(a[v]);
-        if (lane == 0) scr[4 * v + wid] = t;       // virtual warp of virtual thread tid + 128 v
-    }
-    __syncthreads();
-    if (wid == 0) {
-        double t = scr[lane];
-        t = MAX ? warp_max(t) : warp_sum(t);
-        if (lane == 0) scr[32] = t;
-    }
-    __syncthreads();
-    return scr[32];
-}
+// ---- deferred bookkeeping of a batch (see kill_cluster_kernel / shard_commit_cluster_kernel) ------
+// BOOK_BLOCKS extra 128-thread blocks of the first walker launch do the evidence / information
+// update of the batch the walkers are refilling: together they are the 1024 threads of
+// accumulate_kernel (thread vt sums elements vt, vt+1024, ...; warp tree; the 32 warp partials meet
+// in global scratch and the last block to finish reduces them with the same 32-lane tree), so the
+// run stays bit-identical to every other path.  The maximum is order-independent: every block
+// takes it over the whole batch by itself.
+constexpr int BOOK_BLOCKS = 1024 / WALK_THREADS;
 
-__device__ inline void book_accumulate_block(EngineState *S, const WalkParams &P) {
-    static_assert(WALK_THREADS == 128, "8 virtual threads per thread emulate a 1024-thread block");
-    __shared__ double scr[33];
-    const int tid = threadIdx.x;
-    const int k = S->k_cur;
+__device__ inline void book_accumulate_block(EngineState *S, const WalkParams &P, int bb) {
+    __shared__ double scr[5];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = P.book;
     const double logw = S->book_logw, w = S->book_w, m_old = S->M;
-    double a[8];
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        a[v] = -INFINITY;
-        for (int i = tid + WALK_THREADS * v; i < k; i += 1024) {
-            const double lw = logw + P.logl[P.dead_list[i]];
-            if (isfinite(lw)) a[v] = fmax(a[v], lw);
-        }
+    double mx = -INFINITY;
+    for (int i = tid; i < k; i += WALK_THREADS) {
+        const double lw = logw + P.book_vals[P.book_idx[i]];
+        if (isfinite(lw)) mx = fmax(mx, lw);
     }
-    const double mx = block_reduce_v8<true>(a, scr);
+    mx = warp_max(mx);
+    if (lane == 0) scr[wid] = mx;
+    __syncthreads();
+    mx = fmax(fmax(scr[0], scr[1]), fmax(scr[2], scr[3]));
     const double m_new = fmax(m_old, mx);
-    double sz[8], sh[8], zl[8], hl[8];
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        sz[v] = sh[v] = zl[v] = hl[v] = 0.0;
-        for (int i = tid + WALK_THREADS * v; i < k; i += 1024) {
-            const double L = P.logl[P.dead_list[i]];
-            const double lw = logw + L;
-            if (isfinite(lw)) {
-                const double t = exp(lw - m_new);
-                sz[v] += t;
-                sh[v] += t * L;
-            }
-            const double dZ = w * exp(L);
-            zl[v] += dZ;
-            const double dH = dZ * L;
-            if (dH == dH) hl[v] += dH;
+    const int vt = bb * WALK_THREADS + tid;        // virtual thread of the 1024-thread tree
+    double sz = 0.0, sh = 0.0, zl = 0.0, hl = 0.0;
+    for (int i = vt; i < k; i += 1024) {
+        const double L = P.book_vals[P.book_idx[i]];
+        const double lw = logw + L;
+        if (isfinite(lw)) {
+            const double t = exp(lw - m_new);
+            sz += t;
+            sh += t * L;
         }
+        const double dZ = w * exp(L);
+        zl += dZ;
+        const double dH = dZ * L;
+        if (dH == dH) hl += dH;
     }
-    const double szs = block_reduce_v8<false>(sz, scr);
-    const double shs = block_reduce_v8<false>(sh, scr);
-    const double zls = block_reduce_v8<false>(zl, scr);
-    const double hls = block_reduce_v8<false>(hl, scr);
-    if (tid == 0) {
-        if (mx > -INFINITY) {
-            const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
-            S->Zs = S->Zs * scale + szs;
-            S->Hs = S->Hs * scale + shs;
-            S->M = m_new;
+    sz = warp_sum(sz);
+    sh = warp_sum(sh);
+    zl = warp_sum(zl);
+    hl = warp_sum(hl);
+    const int vw = vt >> 5;                        // virtual warp
+    if (lane == 0) {
+        S->book_part[0][vw] = sz;
+        S->book_part[1][vw] = sh;
+        S->book_part[2][vw] = zl;
+        S->book_part[3][vw] = hl;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&S->book_count, 1u) == BOOK_BLOCKS - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (wid == 0) {
+        volatile double *part = &S->book_part[0][0];
+        const double szs = warp_sum(part[lane]), shs = warp_sum(part[32 + lane]);
+        const double zls = warp_sum(part[64 + lane]), hls = warp_sum(part[96 + lane]);
+        if (lane == 0) {
+            if (mx > -INFINITY) {
+                const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+                S->Zs = S->Zs * scale + szs;
+                S->Hs = S->Hs * scale + shs;
+                S->M = m_new;
+            }
+            S->Z_lin += zls;
+            S->H_lin += hls;
+            S->book_count = 0u;
         }
-        S->Z_lin += zls;
-        S->H_lin += hls;
     }
 }
 
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
     const bool after_walk = phase > 0;
     if (!after_walk) { pdl_wait(); pdl_trigger(); }
     const bool book = phase == 0 && P.book != 0;   // this launch also does the batch's deferred bookkeeping
-    if (book && blockIdx.x == gridDim.x - 1) {     // (one extra block; the host only asks when do_walk is certain)
-        book_accumulate_block(S, P);
+    if (book && blockIdx.x + BOOK_BLOCKS >= gridDim.x) {       // (extra blocks; the host only asks when do_walk is certain)
+        book_accumulate_block(S, P, (int)(blockIdx.x + BOOK_BLOCKS - gridDim.x));
         return;
     }
     const bool do_walk = S->do_walk != 0;          // grid-uniform
@@ -511,7 +511,7 @@ struct WalkLauncher {
         int lgG = 0;
         while ((1 << lgG) < G) ++lgG;
         for (int phase = 0; phase <= P.tuning_cycles; ++phase) {
-            const int nb = blocks + (phase == 0 && P.book ? 1 : 0);        // + the bookkeeping block
+            const int nb = blocks + (phase == 0 && P.book ? BOOK_BLOCKS : 0);        // + the bookkeeping blocks
             if (G == 32) GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, true>, dim3(nb), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
             else GL_CUDA(launch_pdl(walk_reg_kernel<Like, D, false>, dim3(nb), dim3(WALK_THREADS), smem, st, P, M, phase, lgG));
         }
