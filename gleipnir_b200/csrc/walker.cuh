@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         wv[j] = phase_width(S, j, phase, k);
-        hw[j] = -0.5 * wv[j];
+        hw[j] = normal ? -0.0 : -0.5 * wv[j];      // x + (-0) == x exactly, for every x
     }
 
     if (active) {
@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
 #pragma unroll
         for (int j = 0; j < D; ++j) accr[j] = 0u;
 
+        // shared-window addresses of the walker's two rings, computed once (the generic->shared
+        // conversion otherwise sits at the head of every round's dependent chain)
+        const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(sb), ub32 = (uint32_t)__cvta_generic_to_shared(ub);
+        bool all_uniform = true;
+#pragma unroll
+        for (int i = 0; i < D; ++i) all_uniform = all_uniform && kindv[i] == GL_PRIOR_UNIFORM;
         int m = 0;
         while (m < n_moves) {                      // group-uniform
             if (m + G > base + CH) fill_ring(m);
@@ -423,17 +429,29 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
             double nj = 0.0, Lt = 0.0, cnew = 0.0;
             if (mine < n_moves) {
                 const int j = (int)((uint32_t)mine % (uint32_t)D);
+                const uint32_t off = (uint32_t)(mine - base) * 8u;
+                double r;
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(sb32 + off) : "memory");
                 const double xj = reg_sel<D>(x, j);
-                // uniform: r*w + (x - w/2)   normal: ndtri(r)*w + x     (samplers.py:100,102)
-                const double loc = normal ? xj : __dadd_rn(xj, reg_sel<D>(hw, j));
-                nj = __dadd_rn(__dmul_rn(sb[mine - base], reg_sel<D>(wv, j)), loc);
-                int kind = kindv[0];
+                // uniform: r*w + (x - w/2)   normal: ndtri(r)*w + x     (samplers.py:100,102); hw = -0 for normal
+                const double loc = __dadd_rn(xj, reg_sel<D>(hw, j));
+                nj = __dadd_rn(__dmul_rn(r, reg_sel<D>(wv, j)), loc);
+                bool pa;
+                if (all_uniform) {                 // block-uniform: the common case needs no acceptance uniform
+                    const double t = nj - reg_sel<D>(p0v, j);
+                    pa = t >= 0.0 && t <= reg_sel<D>(p1v, j);
+                } else {
+                    double u;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(u) : "r"(ub32 + off) : "memory");
+                    int kind = kindv[0];
 #pragma unroll
-                for (int i = 1; i < D; ++i) kind = j == i ? kindv[i] : kind;
-                if (prior_accept(kind, reg_sel<D>(p0v, j), reg_sel<D>(p1v, j), xj, nj, ub[mine - base])) {
-                    Lt = like.template trial_reg<D>(c, j, nj, cnew);
-                    ok = Lt > lstar;
+                    for (int i = 1; i < D; ++i) kind = j == i ? kindv[i] : kind;
+                    pa = prior_accept(kind, reg_sel<D>(p0v, j), reg_sel<D>(p1v, j), xj, nj, u);
                 }
+                // the trial is evaluated by every lane (no divergent region to reconverge from): a
+                // proposal outside the prior is a finite number, its logL is simply not used
+                Lt = like.template trial_reg<D>(c, j, nj, cnew);
+                ok = pa && Lt > lstar;
             }
             const unsigned bal = __ballot_sync(gmask, ok) & gmask;
             if (bal == 0u) {
