@@ -9,7 +9,7 @@
 // copy torch already loaded.
 #include <dlfcn.h>
 #include <nccl.h>
-#include "common.cuh"
+#include "engine.cuh"
 
 struct gl_comm {
     ncclComm_t comm;
@@ -18,6 +18,13 @@ struct gl_comm {
     double *recv;        // [world*cap]  gathered
     double *keys;        // [world*cap]  ordering-key scratch of the fused commit kernel
     size_t cap;
+    // peer-memory exchange of the fused step (gl_comm_p2p_*): one allocation per rank,
+    // [64 arrival flags (u32) | 2 x world*p2p_cap doubles], opened on every peer through CUDA IPC
+    void *p2p_local;
+    void *p2p_peer[gl::GL_MAX_PEERS];
+    gl::PeerTables tables;
+    bool p2p_ready;
+    unsigned int epoch;  // steps exchanged so far (identical on every rank)
 };
 
 namespace gl {
@@ -98,6 +105,8 @@ extern "C" int32_t gl_ns_shard_candidate_count(int32_t k, int32_t world, int64_t
 extern "C" int64_t gl_ns_local_population(const gl_ns *ns);
 extern "C" void gl_ns_internal_sharded_loop(gl_ns *ns, int on);
 extern "C" void gl_ns_internal_commit_refills(gl_ns *ns, int yes);
+extern "C" int gl_ns_internal_shard_step_p2p(gl_ns *ns, const gl::PeerTables *tables, int32_t world, int32_t rank,
+                                             int32_t k, int32_t m, uint32_t epoch, void *stream);
 
 extern "C" {
 
@@ -125,6 +134,10 @@ int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, gl_comm
     c->rank = rank;
     c->send = c->recv = c->keys = nullptr;
     c->cap = 0;
+    c->p2p_local = nullptr;
+    for (int p = 0; p < gl::GL_MAX_PEERS; ++p) c->p2p_peer[p] = nullptr;
+    c->p2p_ready = false;
+    c->epoch = 0;
     ncclResult_t r = gl::nccl().CommInitRank(&c->comm, world, id, rank);
     if (r != ncclSuccess) {
         delete c;
@@ -139,10 +152,55 @@ int gl_comm_destroy(gl_comm *c) {
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
     if (c->keys) cudaFree(c->keys);
+    for (int p = 0; p < c->world && p < gl::GL_MAX_PEERS; ++p)
+        if (p != c->rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+    if (c->p2p_local) cudaFree(c->p2p_local);
     if (c->comm) gl::nccl().CommDestroy(c->comm);
     delete c;
     return GL_OK;
 }
+
+// ---- peer-memory exchange (fused sharded step) ------------------------------------------------------
+// 1. every rank: gl_comm_p2p_alloc -> its CUDA IPC handle;  2. the host all-gathers the handles (any
+// transport);  3. every rank: gl_comm_p2p_open maps the peers' buffers (NVLink peer access).  A barrier
+// between 3 and the first step keeps a fast rank from writing into a buffer that is still being zeroed.
+int gl_comm_p2p_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+static size_t p2p_bytes(int world, size_t cap) { return 256 + 2 * sizeof(double) * (size_t)world * cap; }
+
+int gl_comm_p2p_alloc(gl_comm *c, int64_t cap, uint8_t *handle_out) {
+    GL_REQUIRE(c != nullptr && handle_out != nullptr && cap >= 1, "bad argument");
+    GL_REQUIRE(c->world <= gl::GL_MAX_PEERS, "world=%d > %d peers", c->world, gl::GL_MAX_PEERS);
+    GL_REQUIRE(c->p2p_local == nullptr, "peer buffers already allocated");
+    const size_t bytes = p2p_bytes(c->world, (size_t)cap);
+    GL_CUDA(cudaMalloc(&c->p2p_local, bytes));
+    GL_CUDA(cudaMemset(c->p2p_local, 0, bytes));
+    GL_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    GL_CUDA(cudaIpcGetMemHandle(&h, c->p2p_local));
+    memcpy(handle_out, &h, sizeof(h));
+    c->tables.cap = cap;
+    return GL_OK;
+}
+
+int gl_comm_p2p_open(gl_comm *c, const uint8_t *handles_all) {
+    GL_REQUIRE(c != nullptr && handles_all != nullptr && c->p2p_local != nullptr, "bad argument / alloc first");
+    for (int p = 0; p < c->world; ++p) {
+        void *base = c->p2p_local;
+        if (p != c->rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles_all + (size_t)p * sizeof(h), sizeof(h));
+            GL_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            c->p2p_peer[p] = base;
+        }
+        c->tables.flags[p] = reinterpret_cast<unsigned int *>(base);
+        c->tables.gather[p] = reinterpret_cast<double *>(reinterpret_cast<char *>(base) + 256);
+    }
+    c->p2p_ready = true;
+    return GL_OK;
+}
+
+int gl_comm_p2p_ready(const gl_comm *c) { return c != nullptr && c->p2p_ready ? 1 : 0; }
 
 int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream) {
     GL_REQUIRE(c != nullptr && send_dev != nullptr && recv_dev != nullptr && count >= 1, "bad argument");
@@ -174,11 +232,19 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
         }
         first = false;
         const int32_t m = gl_ns_shard_candidate_count(k, c->world, n_local, candidate_sigmas);
+        gl_ns_internal_commit_refills(ns, done + k < n_deaths_total ? 1 : 0);
+        if (c->p2p_ready && m <= c->tables.cap && n_local <= 196608 && (int64_t)c->world * m <= 196608) {
+            // fused step: candidates, exchange over NVLink peer memory and commit in ONE launch
+            c->epoch += 1;
+            rc = gl_ns_internal_shard_step_p2p(ns, &c->tables, c->world, c->rank, k, m, c->epoch, stream);
+            if (rc) return rc;
+            done += k;
+            continue;
+        }
         rc = gl_ns_shard_candidates(ns, m, c->send, stream);
         if (rc) return rc;
         rc = gl::comm_all_gather(c, c->send, c->recv, (size_t)m, st);
         if (rc) return rc;
-        gl_ns_internal_commit_refills(ns, done + k < n_deaths_total ? 1 : 0);
         rc = gl_ns_shard_commit_truncated(ns, c->recv, c->world, c->rank, k, m, c->keys, stream);
         if (rc) return rc;
         done += k;

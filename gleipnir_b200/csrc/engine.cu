@@ -1089,6 +1089,22 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
     cluster.sync();                                              // nobody exits while its mailbox may still be read
 }
 
+// Rank boundaries of the ascending `positions[0..k)` (gathered index = source rank * m + i):
+// bound[r] = first index whose position belongs to rank >= r, r = 0..world.  One parallel pass with
+// one global round trip (a binary search per boundary is ~22 dependent L2 loads, ~7 us).
+__device__ __forceinline__ void shard_rank_bounds(const long long *__restrict__ positions, int k, int m, int world,
+                                                  int *bound /* shared, world+1 */) {
+    const int tid = threadIdx.x;
+    if (tid <= world) bound[tid] = k;
+    __syncthreads();
+    for (int i = tid; i < k; i += blockDim.x) {
+        const int r = (int)((unsigned int)positions[i] / (unsigned int)m);
+        const int rprev = i > 0 ? (int)((unsigned int)positions[i - 1] / (unsigned int)m) : -1;
+        for (int q = rprev + 1; q <= r; ++q) bound[q] = i;
+    }
+    __syncthreads();
+}
+
 // ---- sharded step on a cluster: candidates and commit ---------------------------------------------
 __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) shard_candidates_cluster_kernel(
     EngineState *S, int end_walk_tc /* >= 0: first finish the previous refill */, long long evals_per_walker, int d,
@@ -1143,7 +1159,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     extern __shared__ unsigned long long keys[];
     __shared__ ClusterSelSmem sm;
     __shared__ double scratch[33];
-    __shared__ int s_start, s_end;
+    __shared__ int s_bound[GL_MAX_PEERS + 1];
     const int tid = threadIdx.x;
     pdl_wait();
     pdl_trigger();
@@ -1157,14 +1173,9 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(gathered[lo_g + i]);
     __syncthreads();
     const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, n, k, positions, nullptr);
-    if (c == 0 && m < k && tid >= 32 && tid < 32 + world && shard_exchange_overflowed(positions, k, m, tid - 32))
-        S->shard_overflow = 1;
-    if (tid == 0) {                                              // this rank's contiguous share of `positions`
-        s_start = lower_bound_pos(positions, k, (long long)rank * m);
-        s_end = lower_bound_pos(positions, k, (long long)(rank + 1) * m);
-    }
-    __syncthreads();
-    const int start = s_start, n_own = s_end - s_start;
+    shard_rank_bounds(positions, k, m, world, s_bound);          // every rank's contiguous share of `positions`
+    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) S->shard_overflow = 1;
+    const int start = s_bound[rank], n_own = s_bound[rank + 1] - s_bound[rank];
     const double logw = logX0 - log(n_global + 1.0);
     const double w = exp(logw);
     const bool room = base_row + n_own <= capacity;
@@ -1226,6 +1237,153 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
             S->lstar = key_to_double(kstar);
             S->k_cur = n_own;
             S->do_walk = 1;
+        }
+    }
+    cluster.sync();
+}
+
+// ---- fused sharded step over NVLink peer memory ----------------------------------------------------
+// candidates -> exchange -> commit in ONE launch, no NCCL call on the step path: the cluster selects
+// this rank's m worst, STORES their logL straight into every peer's exchange buffer (peer pointers
+// from CUDA IPC, comm.cu), fences, raises its arrival flag on every peer (st.release.sys), waits for
+// the world's flags on its own (ld.acquire.sys), and runs the global selection on what arrived.
+// Buffers are double-buffered by epoch parity: a rank can be at most one step ahead of the slowest
+// (its next arrival wait needs everybody's next flag), so a buffer is never overwritten while read.
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) shard_step_p2p_kernel(
+    EngineState *S, int end_walk_tc, long long evals_per_walker, int N, int m, int world, int rank, int k, int d,
+    long long row_offset, double n_global, long long capacity, PeerTables T, unsigned int epoch,
+    long long *__restrict__ cand_list, long long *__restrict__ positions, const double *__restrict__ live,
+    const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
+    double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
+    long long *__restrict__ dead_idx, int *__restrict__ dead_step, int defer_book) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    extern __shared__ unsigned long long keys[];
+    __shared__ ClusterSelSmem sm;
+    __shared__ double scratch[33];
+    __shared__ int s_bound[GL_MAX_PEERS + 1];
+    const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    const int kp = S->k_cur;
+    const int step_now = S->step + (end_walk_tc >= 0 ? 1 : 0);
+    const long long n_dead0 = S->n_dead, base_row = S->n_rows;
+    const double logX0 = S->logX, m_old = S->M;
+    if (end_walk_tc >= 0) {                                      // end_walk_kernel's job, spread over the cluster
+        for (int i = c * KC_THREADS + tid; i < kp; i += KC_CTAS * KC_THREADS) is_dead[dead_list[i]] = 0;
+        if (c == 0) {
+            const double wnew = tid < d ? phase_width(S, tid, end_walk_tc, kp) : 0.0;
+            __syncthreads();
+            if (tid < d) {
+                S->widths[tid] = wnew;
+                for (int q = 0; q < end_walk_tc; ++q) S->acc[q][tid] = 0u;
+            }
+        }
+    }
+    // ---- local candidates ------------------------------------------------------------------------------
+    {
+        const int Nc = (N + KC_CTAS - 1) / KC_CTAS;
+        const int lo_g = c * Nc;
+        const int n_loc = N - lo_g < 0 ? 0 : (N - lo_g < Nc ? N - lo_g : Nc);
+        for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(logl[lo_g + i]);
+        __syncthreads();
+        (void)cluster_select_kworst(cluster, sm, keys, N, m, cand_list, nullptr);
+    }
+    // ---- exchange over peer memory ---------------------------------------------------------------------
+    const long long buf_off = (long long)(epoch & 1u) * (long long)world * T.cap;
+    for (int i = c * KC_THREADS + tid; i < m; i += KC_CTAS * KC_THREADS) {
+        const double v = logl[cand_list[i]];
+        for (int p = 0; p < world; ++p) T.gather[p][buf_off + (long long)rank * m + i] = v;
+    }
+    __threadfence_system();
+    cluster.sync();
+    if (c == 0 && tid < world) {
+        st_release_sys(T.flags[tid] + rank, epoch);               // "rank's candidates of this epoch are in your buffer"
+        const unsigned int *mine = T.flags[rank] + tid;
+        const long long t0 = clock64();
+        int timeout = 0;
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {         // flags only grow (wrap-safe compare)
+            __nanosleep(40);
+            if (clock64() - t0 > 20000000000LL) { timeout = 1; break; }    // ~10 s: a peer died
+        }
+        if (timeout) S->shard_overflow = 2;
+    }
+    cluster.sync();
+    // ---- global selection on what arrived ------------------------------------------------------------------
+    const double *gathered = T.gather[rank] + buf_off;
+    const int n = world * m;
+    {
+        const int Nc = (n + KC_CTAS - 1) / KC_CTAS;
+        const int lo_g = c * Nc;
+        const int n_loc = n - lo_g < 0 ? 0 : (n - lo_g < Nc ? n - lo_g : Nc);
+        for (int i = tid; i < n_loc; i += KC_THREADS) keys[i] = sort_key(__ldcg(gathered + lo_g + i));
+        __syncthreads();
+    }
+    const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, n, k, positions, nullptr);
+    shard_rank_bounds(positions, k, m, world, s_bound);          // every rank's contiguous share of `positions`
+    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) S->shard_overflow = 1;
+    const int start = s_bound[rank], n_own = s_bound[rank + 1] - s_bound[rank];
+    const double logw = logX0 - log(n_global + 1.0);
+    const double w = exp(logw);
+    const bool room = base_row + n_own <= capacity;
+    for (int i = c * KC_THREADS + tid; i < n_own; i += KC_CTAS * KC_THREADS) {
+        const long long slot = cand_list[positions[start + i] - (long long)rank * m];
+        dead_list[i] = slot;
+        is_dead[slot] = 1;
+        if (!defer_book && room) {
+            dead_logl[base_row + i] = logl[slot];
+            dead_w[base_row + i] = w;
+            dead_idx[base_row + i] = slot + row_offset;
+            dead_step[base_row + i] = step_now;
+        }
+    }
+    if (!defer_book && room) {
+        for (int e = c * KC_THREADS + tid; e < n_own * d; e += KC_CTAS * KC_THREADS) {
+            const int q = e / d, j = e - q * d;
+            const long long slot = cand_list[positions[start + q] - (long long)rank * m];
+            dead_x[(base_row + q) * d + j] = live[slot * d + j];
+        }
+    }
+    if (c == 0) {
+        double mx = -INFINITY, m_new = m_old, sums[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!defer_book) cta_accumulate_v2(S, positions, gathered, k, logw, w, m_old, scratch, mx, m_new, sums);
+        if (tid == 0) {
+            if (defer_book) {
+                S->book_logw = logw;
+                S->book_w = w;
+                S->book_base_row = base_row;
+                S->book_step = step_now;
+                S->book_room = room ? 1 : 0;
+            } else {
+                if (mx > -INFINITY) {
+                    const double scale = isfinite(m_old) ? exp(m_old - m_new) : 0.0;
+                    S->Zs = S->Zs * scale + sums[0];
+                    S->Hs = S->Hs * scale + sums[1];
+                    S->M = m_new;
+                }
+                S->Z_lin += sums[2];
+                S->H_lin += sums[3];
+            }
+            S->logX = logX0 + log((n_global - (double)k + 1.0) / (n_global + 1.0));
+            S->n_dead = n_dead0 + k;
+            if (room) S->n_rows = base_row + n_own;
+            S->lstar = key_to_double(kstar);
+            S->k_cur = n_own;
+            S->do_walk = 1;
+            if (end_walk_tc >= 0) {
+                S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
+                S->step = step_now;
+            }
         }
     }
     cluster.sync();
@@ -2243,7 +2401,7 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
     cudaStream_t st = (cudaStream_t)stream;
     const double n_global = (double)ns->cfg.global_population;
     (void)keys_scratch;                    // (kept in the ABI; the cluster commit holds its keys in shared memory)
-    if ((long long)world * m <= gl::KC_MAX_N && world <= gl::KC_THREADS - 32 && !ns->force_multipass) {
+    if ((long long)world * m <= gl::KC_MAX_N && world <= gl::GL_MAX_PEERS && !ns->force_multipass) {
         const int smem = (int)(8 * (((long long)world * m + gl::KC_CTAS - 1) / gl::KC_CTAS));
         int rc0 = gl::ensure_smem((const void *)gl::shard_commit_cluster_kernel, smem);
         if (rc0) return rc0;
@@ -2286,6 +2444,47 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
     ns->h_n_dead += k;
     ns->h_k_last = -1;                     // local batch size is only known on the device
     ns->pending_refill = true;
+    return GL_OK;
+}
+
+// comm.cu's fused step (not part of the ABI): candidates + peer-memory exchange + commit in one launch
+int gl_ns_internal_shard_step_p2p(gl_ns *ns, const gl::PeerTables *tables, int32_t world, int32_t rank, int32_t k,
+                                  int32_t m, uint32_t epoch, void *stream) {
+    GL_REQUIRE(ns != nullptr && tables != nullptr, "NULL argument");
+    if (!ns->initialized || ns->finalized || ns->pending_refill) {
+        gl::set_error("shard step: engine not ready (init first / refill the previous batch)");
+        return GL_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = ns->cfg.population_size;
+    const double n_global = (double)ns->cfg.global_population;
+    GL_REQUIRE(N <= gl::KC_MAX_N && (long long)world * m <= gl::KC_MAX_N && world <= gl::GL_MAX_PEERS && m <= tables->cap,
+               "shard step: sizes outside the fused kernel's range");
+    const long long nmax = N > (long long)world * m ? N : (long long)world * m;
+    const int smem = (int)(8 * ((nmax + gl::KC_CTAS - 1) / gl::KC_CTAS));
+    int rc = gl::ensure_smem((const void *)gl::shard_step_p2p_kernel, smem);
+    if (rc) return rc;
+    const int tc_arg = ns->end_walk_deferred ? ns->cfg.tuning_cycles : -1;
+    ns->end_walk_deferred = false;
+    const long long epw = (20LL * ns->cfg.tuning_cycles + ns->cfg.iterations + ns->cfg.burn_in) * ns->d;
+    const bool defer_book = ns->sharded_loop && ns->commit_refills && ns->cfg.tuning_cycles >= 1 &&
+                            !ns->force_smem_walker && ns->d <= gl::model_reg_max_d(ns->model.kind);
+    gl::prof_mark(ns, ns->ev_sel, st);
+    GL_CUDA(gl::launch_pdl(gl::shard_step_p2p_kernel, dim3(gl::KC_CTAS), dim3(gl::KC_THREADS), (size_t)smem, st, ns->S,
+                           tc_arg, epw, (int)N, m, world, rank, k, ns->d, ns->cfg.row_offset, n_global,
+                           ns->cfg.dead_capacity, *tables, epoch, ns->cand_list, ns->positions, ns->buf.live,
+                           ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w,
+                           (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0));
+    gl::prof_mark(ns, ns->ev_sel, st);
+    ns->prof_sel_launches += 1;
+    ns->h_launches += 1;
+    ns->h_n_dead += k;
+    ns->h_k_last = -1;
+    ns->pending_refill = true;
+    ns->book_deferred = defer_book;
+    ns->book_k = k;
+    ns->book_vals = tables->gather[rank] + (long long)(epoch & 1u) * (long long)world * tables->cap;
+    ns->book_idx = ns->positions;
     return GL_OK;
 }
 

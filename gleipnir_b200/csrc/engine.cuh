@@ -40,6 +40,15 @@ struct EngineState {                 // one instance in device memory per engine
     unsigned int book_count;         // book blocks finished (last one combines and resets)
 };
 
+// Peer-memory tables of the fused sharded step (comm.cu): base pointers of every rank's exchange
+// buffer and arrival flags, mapped into this process through CUDA IPC over NVLink.
+constexpr int GL_MAX_PEERS = 16;
+struct PeerTables {
+    double *gather[GL_MAX_PEERS];        // rank p's buffer: [2][world * cap] doubles (double-buffered by epoch parity)
+    unsigned int *flags[GL_MAX_PEERS];   // rank p's arrival flags: [world] epochs
+    long long cap;                       // candidates per rank the buffers were sized for
+};
+
 struct WalkParams {                  // by-value kernel parameter
     EngineState *S;
     const long long *dead_list;      // [k_cur] local slots of the current batch, ascending

@@ -16,9 +16,35 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the chains live
 }
 
+// dependent-issue latency of DFMA: one warp, a chain of `iters` x 8 dependent fmas, clock64 around it
+__global__ void dfma_latency_kernel(double *out, long long *cycles, int iters, double a, double b) {
+    double x = out[threadIdx.x];
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x = fma(x, a, b);
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
 }  // namespace gl
 
 extern "C" {
+
+// Cycles per dependent DFMA seen by a single warp (host-synchronous; scratch_dev: >= 32 doubles + 1 int64).
+int gl_microbench_dfma_latency(int32_t iters, double *scratch_dev, double *cycles_per_dfma_out) {
+    GL_REQUIRE(iters >= 1 && scratch_dev != nullptr && cycles_per_dfma_out != nullptr, "bad argument");
+    long long *cyc = reinterpret_cast<long long *>(scratch_dev + 32);
+    GL_CUDA(cudaMemset(scratch_dev, 0, 33 * sizeof(double)));
+    gl::dfma_latency_kernel<<<1, 32>>>(scratch_dev, cyc, iters, 0.999999, 1e-9);
+    GL_CHECK_LAUNCH();
+    long long h = 0;
+    GL_CUDA(cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    *cycles_per_dfma_out = (double)h / ((double)iters * 8.0);
+    return GL_OK;
+}
 
 // Enqueue the DFMA kernel; flops = blocks*256*iters*8*2.  The caller times it with events.
 int gl_microbench_dfma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream) {

@@ -129,7 +129,10 @@ class DeviceEngine(object):
 
     def overflowed(self):
         """True when a truncated candidate exchange could not prove one of its steps exact."""
-        return bool(self.state().shard_overflow)
+        flag = int(self.state().shard_overflow)
+        if flag == 2:
+            raise RuntimeError("sharded run: a peer did not deliver its candidates within 10 s (peer-memory exchange)")
+        return bool(flag)
 
     def final_partial(self):
         torch = _torch()

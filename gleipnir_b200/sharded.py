@@ -123,6 +123,7 @@ class NcclComm(object):
 
         from . import _lib
         self.lib = _lib.load()
+        self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         nbytes = self.lib.gl_comm_unique_id_bytes()
@@ -134,6 +135,41 @@ class NcclComm(object):
         ident = (ctypes.c_uint8 * nbytes).from_buffer_copy(box[0])
         self.h = ctypes.c_void_p()
         _lib.check(self.lib.gl_comm_create(self.world, self.rank, ident, ctypes.byref(self.h)))
+
+    def enable_p2p(self, cap):
+        """Map every rank's exchange buffer into this process (CUDA IPC over NVLink) so that
+        gl_ns_advance_sharded can run its fused one-kernel step; collective.  Returns True when
+        the peer path is ready (False: the NCCL all-gather path stays in use)."""
+        import ctypes
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        if self.lib.gl_comm_p2p_ready(self.h):
+            return True
+        if getattr(self, "_p2p_failed", False) or os.environ.get("GLEIPNIR_B200_NO_P2P") == "1":
+            return False
+        nbytes = self.lib.gl_comm_p2p_handle_bytes()
+        buf = (ctypes.c_uint8 * nbytes)()
+        rc = self.lib.gl_comm_p2p_alloc(self.h, max(int(cap), 16384), buf)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf) if rc == 0 else None, group=self.group)
+        if any(h is None for h in handles):               # some rank could not allocate: nobody uses it
+            self._p2p_failed = True
+            return False
+        allb = b"".join(handles)
+        arr = (ctypes.c_uint8 * len(allb)).from_buffer_copy(allb)
+        rc = self.lib.gl_comm_p2p_open(self.h, arr)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, rc == 0, group=self.group)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if not all(oks):
+            self._p2p_failed = True
+            raise RuntimeError("gl_comm_p2p_open failed on some rank: %s" % (self.lib.gl_last_error() or b"?").decode())
+        return True
 
     def __del__(self):
         h = getattr(self, "h", None)
@@ -221,6 +257,7 @@ def run_sharded_native(engine, nccl_comm, n_deaths, batch_k, candidate_sigmas=DE
     when the truncated one could not prove a step exact; returns True when that happened."""
     from . import _lib
     st = engine._stream()
+    nccl_comm.enable_p2p(batch_k)             # fused one-kernel step over NVLink peer memory when available
 
     def once(sigmas):
         engine.init()

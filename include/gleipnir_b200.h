@@ -279,6 +279,16 @@ GL_API int gl_comm_unique_id(uint8_t *out_bytes);
 GL_API int gl_comm_create(int32_t world, int32_t rank, const uint8_t *id_bytes, gl_comm **out);
 GL_API int gl_comm_destroy(gl_comm *c);
 GL_API int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream);
+/* Peer-memory exchange: with it gl_ns_advance_sharded runs candidates + exchange + commit as ONE
+ * kernel per step that stores the candidates straight into every peer's buffer over NVLink and
+ * synchronises with system-scope flags -- no NCCL call on the step path.  Setup: every rank calls
+ * gl_comm_p2p_alloc (cap >= batch_k candidates per rank) and gets its CUDA IPC handle
+ * (gl_comm_p2p_handle_bytes bytes); the host all-gathers the handles rank-major by any means;
+ * every rank calls gl_comm_p2p_open; one barrier.  Without it the NCCL all-gather path is used. */
+GL_API int gl_comm_p2p_handle_bytes(void);
+GL_API int gl_comm_p2p_alloc(gl_comm *c, int64_t cap, uint8_t *handle_out);
+GL_API int gl_comm_p2p_open(gl_comm *c, const uint8_t *handles_all);
+GL_API int gl_comm_p2p_ready(const gl_comm *c);
 /* Enqueue steps (refill of the waiting batch, candidates, all-gather, commit) until
  * `n_deaths_total` global deaths; `n_dead_so_far` = global deaths already recorded.
  * `candidate_sigmas` > 0 selects the truncated exchange (check gl_ns_state.shard_overflow after
@@ -363,6 +373,8 @@ GL_API int gl_reference_exact_run_host(uint32_t seed, int32_t N, int32_t d, cons
  * MEASURED_PEAKS.json has no FP64 entry).  Enqueues `blocks` CTAs of 256 threads running
  * `iters` x 8 independent DFMAs each; *flops_out = floating-point operations enqueued.
  * `scratch_dev` must hold blocks*256 doubles.  Time it with CUDA events on `stream`. */
+/* cycles per DEPENDENT DFMA for one warp (the walker's chain is bound by this, not by the pipe's throughput) */
+GL_API int gl_microbench_dfma_latency(int32_t iters, double *scratch_dev, double *cycles_per_dfma_out);
 GL_API int gl_microbench_dfma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream);
 /* Same for the FP64 tensor cores: `blocks` CTAs of 8 warps, `iters` x 4 DMMA m8n8k4 per warp. */
 GL_API int gl_microbench_dmma(int32_t blocks, int32_t iters, double *scratch_dev, int64_t *flops_out, void *stream);
