@@ -1784,6 +1784,7 @@ struct gl_ns {
     bool commit_refills;                          // ... and the next commit is followed by a refill
     bool force_smem_walker;                       // tests: generic shared-memory walker even for small d
     bool book_deferred;                           // the last kill / commit left record + accumulate to the next refill
+    int walk_k_max;                               // upper bound of the batch the next refill serves (0: batch_k)
     int book_k;                                   // values of that batch: L(i) = book_vals[book_idx[i]]
     const double *book_vals;
     const long long *book_idx;
@@ -1859,7 +1860,9 @@ static WalkParams walk_params(const gl_ns *ns) {
     P.burn_in = ns->cfg.burn_in;
     P.tuning_cycles = ns->cfg.tuning_cycles;
     P.proposal = ns->cfg.proposal;
-    P.k_max = ns->cfg.batch_k;
+    // sharded: a rank never refills more slots than the candidates it sent (m <= batch_k), so the walker
+    // grid and the lanes per walker are sized for m, not for the global batch
+    P.k_max = ns->walk_k_max > 0 && ns->walk_k_max < ns->cfg.batch_k ? ns->walk_k_max : ns->cfg.batch_k;
     P.lanes = ns->cfg.walker_lanes;
     P.force_smem_state = ns->force_smem_walker ? 1 : 0;
     P.book = ns->book_deferred ? ns->book_k : 0;
@@ -2100,6 +2103,7 @@ int gl_ns_create(const gl_ns_config *cfg, const gl_prior *priors_host, int32_t d
     ns->commit_refills = false;
     ns->force_smem_walker = false;
     ns->book_deferred = false;
+    ns->walk_k_max = 0;
     ns->prof_walk_launches = ns->prof_sel_launches = 0;
     *out = ns;
     return GL_OK;
@@ -2418,6 +2422,7 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
         ns->book_k = k;
         ns->book_vals = gathered_logl_dev;
         ns->book_idx = ns->positions;
+        ns->walk_k_max = m;
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
         ns->prof_sel_launches += 1;
@@ -2444,6 +2449,7 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
     ns->h_n_dead += k;
     ns->h_k_last = -1;                     // local batch size is only known on the device
     ns->pending_refill = true;
+    ns->walk_k_max = m;
     return GL_OK;
 }
 
@@ -2481,6 +2487,7 @@ int gl_ns_internal_shard_step_p2p(gl_ns *ns, const gl::PeerTables *tables, int32
     ns->h_n_dead += k;
     ns->h_k_last = -1;
     ns->pending_refill = true;
+    ns->walk_k_max = m;
     ns->book_deferred = defer_book;
     ns->book_k = k;
     ns->book_vals = tables->gather[rank] + (long long)(epoch & 1u) * (long long)world * tables->cap;
