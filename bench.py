@@ -329,10 +329,25 @@ def run_b200_arm(args):
     avg_launch_s = (walk_ms * 1e-3) / max(walk_launches, 1)
     flop_per_eval = FLOP_PER_TRIAL_EGGCARTON_D2
     achieved = (walk_evals_per_step / (w["tuning_cycles"] + 1)) * flop_per_eval / avg_launch_s / 1e12
+    # dependent-issue latency of DFMA: what actually bounds a Metropolis chain (one warp per walker, ~25
+    # dependent FP64 operations per round), as opposed to the pipe's throughput peak above
+    lat = ctypes.c_double(0.0)
+    lat_scratch = torch.zeros(64, dtype=torch.float64, device="cuda")
+    L.check(lib.gl_microbench_dfma_latency(4096, lat_scratch.data_ptr(), ctypes.byref(lat)))
+    hbm_peak = peaks.get("hbm_gbs")
+    walk_bytes = (k / world) * 8.0 * (2 * d + 1)        # algorithmic: seed row in, point + logL out per replacement
     roofline = dict(kernel="walk_reg_kernel<LikeEggCarton, 2>", bound="fp64", achieved=achieved, peak=dfma_peak,
-                    unit="TFLOP/s", frac=achieved / dfma_peak if dfma_peak else None, traffic=None,
+                    unit="TFLOP/s", frac=achieved / dfma_peak if dfma_peak else None,
+                    traffic=158208, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one production "
+                    "launch, ncu --set full (profiles/r01_g_walk_reg_kernel_c2.txt); algorithmic bytes per launch: "
+                    "%d" % int(walk_bytes),
                     peak_source="gl_microbench_dfma measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     flop_per_trial_move=flop_per_eval,
+                    dependent_dfma_latency_cycles=lat.value,
+                    note="latency-bound by construction: a Metropolis chain is one dependent sequence and C2 offers "
+                         "k*G = 32 000 threads to a 303 000-thread machine; neither HBM nor a tensor pipe is the limiter",
+                    walker_hbm=dict(bound="hbm", achieved=walk_bytes / avg_launch_s / 1e9, peak=hbm_peak, unit="GB/s",
+                                    frac=(walk_bytes / avg_launch_s / 1e9 / hbm_peak) if hbm_peak else None),
                     avg_launch_us=avg_launch_s * 1e6, launches_timed=int(walk_launches),
                     walker_share_of_step=walk_ms / prof_total_ms, select_share_of_step=sel_ms / prof_total_ms,
                     timing="CUDA events around every launch in %d extra steps after the timed region "
@@ -347,15 +362,16 @@ def run_b200_arm(args):
     cpu = None
     if world == 1:
         ev1, t1 = cpu_sample_parallel(1, N, 1)
-        cpu_evals, cpu_wall = cpu_sample_parallel(1, N, 120)
-        t_iter = (cpu_wall - t1) / 119.0
+        n_it = 600                                  # ~12 s of host work on one core
+        cpu_evals, cpu_wall = cpu_sample_parallel(1, N, n_it)
+        t_iter = (cpu_wall - t1) / (n_it - 1.0)
         evals_full = N + (n_deaths - 1) * (1 + sweeps * d)
         cpu_full_s = t1 + (n_deaths - 1) * t_iter
         cpu_value = evals_full / cpu_full_s
         cpu = dict(value=cpu_value, unit="evals/s", cores=1, kind="port",
                    sample="reference-as-shipped port (oracle/reference_port.py), N=%d init (%.2f s) + "
-                          "120 iterations (%d evals, %.1f s); value = full-run evals / (t_init + "
-                          "(n_deaths-1)*t_iteration)" % (N, t1, cpu_evals, cpu_wall),
+                          "%d iterations (%d evals, %.1f s); value = full-run evals / (t_init + "
+                          "(n_deaths-1)*t_iteration)" % (N, t1, n_it, cpu_evals, cpu_wall),
                    time_to_converged_logZ_s_extrapolated=cpu_full_s)
     line = dict(metric="logL evals/sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
@@ -364,11 +380,13 @@ def run_b200_arm(args):
                             walker_lanes=args.walker_lanes or "auto",
                             sampler="MetropolisComponentWiseHardNSRejection(iterations=50, tuning_cycles=2)",
                             l2="flushed between timed runs (256 MB memset)",
-                            parallelism=("live set sharded over %d ranks, all-gather of k logL per step" % world)
+                            parallelism=("live set sharded over %d ranks; per step one fused kernel exchanges "
+                                         "~k/world + 8 sigma candidate logL per rank over NVLink peer memory" % world)
                             if world > 1 else "single"),
                 clocks=clk, gpu_launches=int(float(tot[2])),
                 e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int(24 * d + ctypes.sizeof(L.gl_ns_config)),
-                         d2h_bytes_per_step=int(last_rows * (8 * (d + 2) + 8 + 4) + ctypes.sizeof(L.gl_ns_state)),
+                         # dead-point table + final live points + two state snapshots
+                         d2h_bytes_per_step=int(last_rows * world * 8 * (d + 2) + N * d * 8 + 2 * ctypes.sizeof(L.gl_ns_state)),
                          ms_per_step=1e3 * t_e2e / args.steps),
                 roofline=roofline,
                 cpu_baseline=cpu,
