@@ -106,6 +106,7 @@ _SIGNATURES = {
     "gl_comm_p2p_alloc": (c_int, [_P, c_int64, POINTER(ctypes.c_uint8)]),
     "gl_comm_p2p_open": (c_int, [_P, POINTER(ctypes.c_uint8)]),
     "gl_comm_p2p_ready": (c_int, [_P]),
+    "gl_comm_p2p_disable": (c_int, [_P]),
     "gl_microbench_dfma_latency": (c_int, [c_int32, _P, POINTER(c_double)]),
     "gl_export_gathered_table": (c_int, [_P, _P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P]),
     "gl_ns_force_smem_walker": (c_int, [_P, c_int32]),

@@ -202,6 +202,13 @@ int gl_comm_p2p_open(gl_comm *c, const uint8_t *handles_all) {
 
 int gl_comm_p2p_ready(const gl_comm *c) { return c != nullptr && c->p2p_ready ? 1 : 0; }
 
+// every rank must take the same path: when mapping failed anywhere, everybody falls back to NCCL
+int gl_comm_p2p_disable(gl_comm *c) {
+    GL_REQUIRE(c != nullptr, "comm is NULL");
+    c->p2p_ready = false;
+    return GL_OK;
+}
+
 int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev, int64_t count, void *stream) {
     GL_REQUIRE(c != nullptr && send_dev != nullptr && recv_dev != nullptr && count >= 1, "bad argument");
     return gl::comm_all_gather(c, send_dev, recv_dev, (size_t)count, (cudaStream_t)stream);

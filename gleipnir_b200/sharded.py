@@ -166,9 +166,14 @@ class NcclComm(object):
         dist.all_gather_object(oks, rc == 0, group=self.group)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        if not all(oks):
+        if not all(oks):                                  # every rank takes the same path: NCCL all-gather
+            import warnings
             self._p2p_failed = True
-            raise RuntimeError("gl_comm_p2p_open failed on some rank: %s" % (self.lib.gl_last_error() or b"?").decode())
+            self.lib.gl_comm_p2p_disable(self.h)
+            if rc != 0:
+                warnings.warn("peer-memory exchange unavailable (%s); using the NCCL all-gather path"
+                              % (self.lib.gl_last_error() or b"?").decode())
+            return False
         return True
 
     def __del__(self):

@@ -289,6 +289,7 @@ GL_API int gl_comm_p2p_handle_bytes(void);
 GL_API int gl_comm_p2p_alloc(gl_comm *c, int64_t cap, uint8_t *handle_out);
 GL_API int gl_comm_p2p_open(gl_comm *c, const uint8_t *handles_all);
 GL_API int gl_comm_p2p_ready(const gl_comm *c);
+GL_API int gl_comm_p2p_disable(gl_comm *c);   /* collective decision of the host: all ranks use the NCCL path */
 /* Enqueue steps (refill of the waiting batch, candidates, all-gather, commit) until
  * `n_deaths_total` global deaths; `n_dead_so_far` = global deaths already recorded.
  * `candidate_sigmas` > 0 selects the truncated exchange (check gl_ns_state.shard_overflow after
