@@ -538,6 +538,7 @@ struct WalkLauncher {
     template <class Like>
     int operator()() {
         int G = walker_group_size(P.k_max, P.lanes);
+        if (P.lanes < 1 && G < min_lanes<Like>::value) G = min_lanes<Like>::value;   // several waves beat one lane
         if constexpr (reg_max_d<Like>::value > 0) {
             if (!P.force_smem_state && P.d <= reg_max_d<Like>::value) {
                 switch (P.d) {

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--tuning-cycles", type=int, default=1)
     ap.add_argument("--cutoff-nats", type=float, default=160.0, help="stop when ln X <= -cutoff")
     ap.add_argument("--dim", type=int, default=50)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per walker (0 = automatic)")
     a = ap.parse_args()
     import torch
     from gleipnir_b200 import likelihoods as lk
@@ -28,7 +29,7 @@ def main():
     n_deaths = int(a.cutoff_nats * N)
     # keep only the scalar outputs: the dead log of a C3-scale run is tens of GB
     eng = DeviceEngine([(0, -5.0, 10.0)] * d, like.device_model(), N, k, min(n_deaths, 2 * k), iterations=a.iterations,
-                       tuning_cycles=a.tuning_cycles, seed=1)
+                       tuning_cycles=a.tuning_cycles, seed=1, walker_lanes=a.lanes)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     eng.init()
