@@ -180,3 +180,20 @@ def test_unprovable_truncated_step_raises_the_flag_and_the_run_is_repeated_in_fu
     auto = _shards(world, n, k)
     run_sharded(auto, LocalComm(world), deaths, k, candidate_sigmas=1e-9)
     assert _result_key(auto) == _result_key(full)
+
+
+def test_gloo_world_size_2_with_a_truncated_exchange(tmp_path):
+    """k = 200 over 2 ranks: m = 165 < k candidates per rank travel over gloo; same tables as the
+    in-process emulation with the FULL exchange."""
+    import torch.multiprocessing as mp
+    from gleipnir_b200.sharded import _run_sharded_once, candidate_count
+    n, k, deaths, world = 800, 200, 600, 2
+    assert candidate_count(k, world, n // world, 8.0) == 165
+    mp.spawn(_gloo_worker, args=(world, _free_port(), n, k, deaths, str(tmp_path)), nprocs=world, join=True)
+    shards = _shards(world, n, k)
+    _run_sharded_once(shards, LocalComm(world), deaths, k, 0.0)
+    for r, sh in enumerate(shards):
+        got = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(got["dead"], sh.result["dead"])
+        assert np.array_equal(got["idx"], sh.result["dead_index"])
+        assert float(got["logZ"]) == sh.result["logZ"] and float(got["info"]) == sh.result["information"]
