@@ -819,21 +819,32 @@ __device__ unsigned long long cluster_select_kworst(cooperative_groups::cluster_
             X.hist[par][tid] = t;
         }
         cluster.sync();
-        if (tid < 16) {
+        if (wid == 0) {
+            // one warp sums the cluster's counts per digit (lane = digit), scans them with shuffles and
+            // publishes the decision: first digit whose running count reaches k_rem, the count below it
+            // and the bucket size (a redundant 16-step scan in every thread was 37 % of a pass)
             unsigned int t = 0u;
+            if (lane < 16) {
 #pragma unroll
-            for (int r = 0; r < KC_CTAS; ++r) t += cluster.map_shared_rank(&X, r)->hist[par][tid];
-            tot[tid] = t;
+                for (int r = 0; r < KC_CTAS; ++r) t += cluster.map_shared_rank(&X, r)->hist[par][lane];
+            }
+            unsigned int incl = t;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned int hit = __ballot_sync(0xffffffffu, lane < 16 && (int)incl >= k_rem);
+            const int dg = hit ? __ffs(hit) - 1 : 15;
+            const unsigned int incl_d = __shfl_sync(0xffffffffu, incl, dg), t_d = __shfl_sync(0xffffffffu, t, dg);
+            if (lane == 0) {
+                tot[0] = (unsigned int)dg;
+                tot[1] = incl_d - t_d;
+                tot[2] = t_d;
+            }
         }
         __syncthreads();
-        int run = 0, digit = 15, run_at = 0, c_at = 0;
-        bool found = false;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int cq = (int)tot[q];
-            if (!found && run + cq >= k_rem) { found = true; digit = q; run_at = run; c_at = cq; }
-            run += cq;
-        }
+        const int digit = (int)tot[0], run_at = (int)tot[1], c_at = (int)tot[2];
         prefix = (prefix << 4) | (unsigned long long)digit;
         k_rem -= run_at;
         sel_shift = shift;
