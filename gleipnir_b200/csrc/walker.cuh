@@ -377,22 +377,41 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_reg_kernel(WalkParams P, Mo
             }
         }
         if (from_seed) {
+            // survivor pick, redrawn while it hits a dead slot.  The first draw's dead flag and seed row
+            // are requested BEFORE the ring is filled and consumed after it, so the two dependent L2
+            // round trips hide behind the ~600 instructions of Philox; only a redraw (probability k/N)
+            // pays them again.
             long long pick = 0;
-            if (lane == 0) {
-                for (uint32_t a = 0;; ++a) {       // survivor pick, redraw while dead
-                    const U2 u = philox_uniforms(P.seed, g, step, a, GL_TAG_PICK);
-                    pick = (long long)(u.a * (double)P.N);
-                    if (pick >= P.N) pick = P.N - 1;
-                    if (!P.is_dead[pick]) break;
-                }
+            {
+                const U2 u = philox_uniforms(P.seed, g, step, 0u, GL_TAG_PICK);    // same value in every lane
+                pick = (long long)(u.a * (double)P.N);
+                if (pick >= P.N) pick = P.N - 1;
             }
-            pick = __shfl_sync(gmask, pick, gbase);
-            const double *src = P.live + pick * D;
+            const unsigned char dead0 = P.is_dead[pick];
+            {
+                const double *src = P.live + pick * D;
 #pragma unroll
-            for (int j = 0; j < D; ++j) x[j] = src[j];
+                for (int j = 0; j < D; ++j) x[j] = src[j];
+            }
+            fill_ring(0);
+            if (dead0) {                           // group-uniform
+                if (lane == 0) {
+                    for (uint32_t a = 1;; ++a) {
+                        const U2 u = philox_uniforms(P.seed, g, step, a, GL_TAG_PICK);
+                        pick = (long long)(u.a * (double)P.N);
+                        if (pick >= P.N) pick = P.N - 1;
+                        if (!P.is_dead[pick]) break;
+                    }
+                }
+                pick = __shfl_sync(gmask, pick, gbase);
+                const double *src = P.live + pick * D;
+#pragma unroll
+                for (int j = 0; j < D; ++j) x[j] = src[j];
+            }
             L = like.template init_reg<D>(x, c);
+        } else {
+            fill_ring(0);
         }
-        fill_ring(0);
     }
     if (after_walk) { pdl_wait(); pdl_trigger(); }
     __syncthreads();                               // acc_s cleared
