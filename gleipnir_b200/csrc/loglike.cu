@@ -142,6 +142,13 @@ int gl_model_create_external(int32_t d, void *walk_fn, void *eval_fn, const void
     }
     m->dev.aux0 = m->aux_alloc;
     m->dev.n_aux = (int32_t)(blob_bytes / 8);
+    // host-visible launch hints: header words 8..10 of the blob (ode_coop.cuh: number of conditions, ...)
+    if (blob_bytes >= 11 * 8) {
+        const double *hb = (const double *)blob_host;
+        m->dev.s0 = hb[8];
+        m->dev.s1 = hb[9];
+        m->dev.s2 = hb[10];
+    }
     m->dev.ext_walk = (int (*)(const void *, const void *, void *))walk_fn;
     m->dev.ext_eval = (int (*)(const void *, const double *, long long, double *, void *))eval_fn;
     return GL_OK;

@@ -1,177 +1,413 @@
-// Cooperative ODE solver for mid-size mass-action networks (4 < NS <= 32 species).
+// Cooperative ODE solver for mass-action networks above 4 species, and the multi-condition
+// likelihood protocol on top of it.
 //
 // A thread-per-system Rosenbrock solve keeps an NS x NS matrix in thread-local memory (9 KB stack
 // frame at NS = 16; measured 145 us per step, 0.2-1.4 s per solve) -- fine for throughput, useless
 // for a Metropolis chain that needs hundreds of DEPENDENT solves.  Here a group of GL lanes
-// (16 or 32, GL >= NS) owns one system:
-//   * lane i holds species i: y_i, the stage vectors and ROW i of M = I/(gamma h) - J in registers;
-//   * the network is data, not code (generated tables: reactant slots, rate constants, CSR rows of
-//     the stoichiometric matrix), so all lanes run the same instructions: lanes evaluate reaction
-//     rates in parallel, then each lane gathers its own row of f and J from shared memory;
-//   * LU (no pivoting: M is the identity plus a small multiple of a kinetics Jacobian, the same
-//     assumption KPP-style chemistry solvers make; a vanishing/non-finite pivot fails the step) and
-//     the four triangular solves of a Kaps-Rentrop step run over warp shuffles with compile-time
-//     column loops, so the matrix never leaves registers.
-// Same method, coefficients, step control and misfit forms as ode_like.cuh (thread-per-system).
+// (16 or 32) owns one system:
+//   * lane i holds CORE species i: y_i, the stage vectors and ROW i of M = I/(gamma h) - J in
+//     registers.  A network with more species than lanes keeps NX = NS - 32 mutually independent
+//     low-degree LEAF species in a second register slot of lanes 0..NX-1; their rows stay in shared
+//     memory and are eliminated first (block elimination), so the register matrix stays 32 wide;
+//   * species order, the leaf set, the symbolic LU (with fill) and the level schedules of the
+//     triangular solves are decided ONCE per network by gleipnir_b200/odeplan.py and emitted as
+//     straight-line code (Net::lu, Net::solve): one shuffle + one FMA per structural nonzero of a
+//     pivot row, nothing for structural zeros;
+//   * reaction rates are evaluated by all lanes in parallel into shared memory, then each lane
+//     gathers its own row of f and J (CSR rows of the stoichiometric matrix);
+//   * no pivoting: M is the identity plus a small multiple of a kinetics Jacobian, the same
+//     assumption KPP-style chemistry solvers make; a vanishing/non-finite pivot fails the step
+//     (the step is retried with h/10).
+// Same method (Kaps-Rentrop 4(3), Shampine's parameters), step control and misfit forms as
+// ode_like.cuh (thread-per-system, NS <= 4).
+//
+// Protocol (blob layout ProtoBlob, written by odegen.py::pack_protocol_blob) -- the structure of
+// examples/pysb_jarm/run_jarm_multinest.py:92-143, of which the single-condition likelihoods of
+// pysb_utilities/nestedsample_it.py:273-339 are the special case "one condition, no
+// pre-equilibration, no cycle terms":
+//     params[mask] = 10**Y                                                       (:94)
+//     cycle products scored by norm(loc, scale).logpdf, NaN -> -inf              (:72-90, 101-103)
+//     per condition: parameter overrides                                          (:110-111, 122-123)
+//         pre-equilibration to t_end with the listed constants zeroed; failure -> -inf   (:105-119)
+//         main solve from the equilibrated state, constants restored             (:125)
+//         rows: norm / halfnorm logpdf of observable / scale at the masked times (:126-134)
+//     sum; NaN -> -inf                                                            (:137-143)
+// Conditions are independent solves: the walker gives each its own lane group.
 #pragma once
 #include "common.cuh"
 #include "likelihoods.cuh"
-#include "ode_like.cuh"
 #include "engine.cuh"
 #include "philox.cuh"
 
+// resident 128-thread blocks per SM the kernels are compiled for (register budget 65536 / (128 * blocks));
+// the generator sets it per network (odegen.py)
+#ifndef GL_COOP_MIN_BLOCKS
+#define GL_COOP_MIN_BLOCKS 3
+#endif
+
 namespace gl {
 
-// Net (generated): NS, NP, NR, NOBS, GL; tables
-// accessors (inline functions over __device__ const arrays):
-//   rx_a(r), rx_b(r) (second reactant or -1), rx_k(r) (rate parameter), rx_sf(r) (double)
-//   row_ptr(i), row_rx(z), row_coef(z)               (stoichiometry, CSR by species)
+enum ProtoBlob {
+    PB_NSAMPLED = 0, PB_NPARAMS = 1, PB_NTIMES = 2, PB_LIKE = 3, PB_MAXSTEPS = 4, PB_RTOL = 5, PB_ATOL = 6,
+    PB_NROWS = 7, PB_NCOND = 8, PB_PREEQ = 9, PB_PREEQ_TEND = 10, PB_PREEQ_TOL = 11, PB_NZERO = 12,
+    PB_NCYCLES = 13, PB_CYC_LOC = 14, PB_CYC_SCALE = 15,
+    PB_OFF_NOMINAL = 16, PB_OFF_MAP = 17, PB_OFF_ISLOG = 18, PB_OFF_TSPAN = 19, PB_OFF_ROWMETA = 20,
+    PB_OFF_DATA = 21, PB_OFF_SD = 22, PB_OFF_MASK = 23, PB_OFF_CTERM = 24, PB_OFF_ROWPTR = 25,
+    PB_OFF_OVERPTR = 26, PB_OFF_OVERIDX = 27, PB_OFF_OVERVAL = 28, PB_OFF_ZEROIDX = 29, PB_OFF_CYCPTR = 30,
+    PB_OFF_CYCFAC = 31, PB_OFF_STOPPTR = 32, PB_OFF_STOPS = 33, PB_HEADER = 48
+};
+#ifndef GL_ODE_LIKE_TYPES
+#define GL_ODE_LIKE_TYPES
+enum OdeLikeType { ODE_SNLPDF = 0, ODE_MSE = 1, ODE_SSE = 2 };
+#endif
+enum OdeRowKind { ODE_ROW_NORM = 0, ODE_ROW_HALFNORM = 1 };
+
+// work counters of a plugin (read through gl_plugin_counters): likelihood evaluations actually
+// integrated (prior-rejected trial moves are not), ODE solves, Rosenbrock steps attempted
+struct CoopCounters {
+    unsigned long long evals, solves, steps;
+    unsigned long long next;          // work-claim cursor of the batch-evaluation kernel (zeroed before a launch)
+};
+
+// Net (generated): NS, NC (core rows), NX (leaves), NXA = max(NX,1), NP, NR, NOBS, GL, LD (row stride of J:
+// >= NS, = 2 mod 4), NRM = ceil(NR/GL), NRP = NRM*GL, EF/EF2/EJ/EJ2 (list depths);
+// all species indices in the plan's INTERNAL numbering (core 0..NC-1, leaves NC..NS-1);
+//   rx_k(r) (rate parameter), rx_sf(r) (double)
+//   rtab(r)   = a | b << 16: reactant slots of reaction r in y[] (y[NS] = 1.0 stands in for "no second reactant")
+//   ftab(e*GL + i)            position in sv[] of the e-th term of f_i (padding: the zero slot 2*NRP)
+//   jtab(e*GL + i)            position in sd[] | column << 16 | "first term of this J_i,column" << 24; every entry
+//                             stores the running sum, so the last store of a column holds the full sum
+//   ftab2 / jtab2             the same for the leaf species (width NXA)
 //   init_kind(i) (0 const, 1 parameter), init_val(i) (double), init_par(i)
 //   obs_ptr(o), obs_sp(z), obs_coef(z) (double)
+//   lu(M, A, J, diag, lane, gmask, gbase, inv_d2) -> pivots ok;  solve(M, A, J, inv_d, inv_d2, b, b2, ...)
 template <class Net>
 struct CoopOde {
-    static constexpr int NS = Net::NS, GL = Net::GL, NR = Net::NR;
+    static constexpr int NS = Net::NS, NC = Net::NC, NX = Net::NX, NXA = Net::NXA, GL = Net::GL, NR = Net::NR;
+    static constexpr int LD = Net::LD, NRM = Net::NRM, NRP = Net::NRP;
 
-    struct Shared {                     // per group, in shared memory
-        double y[NS];                   // state broadcast
-        double v[NR];                   // reaction rates
-        double da[NR], db[NR];          // d v_r / d y_a, d v_r / d y_b
-        double J[NS][NS + 1];           // Jacobian rows (+1: bank-conflict padding)
-        double p[Net::NP];              // parameter vector of this system
+    struct alignas(16) Tables {         // per block, in shared memory: the network's index lists
+        unsigned int rtab[NRP];
+        unsigned int jtab[Net::EJ * GL];
+        unsigned int jtab2[Net::EJ2 * NXA];
+        unsigned short ftab[Net::EF * GL];
+        unsigned short ftab2[Net::EF2 * NXA];
+    };
+    struct alignas(16) Shared {         // per group, in shared memory
+        double J[NS * LD];              // Jacobian rows; entries outside the structural pattern stay 0
+        double sv[2 * NRP + 2];         // v_r, -v_r; [2*NRP] = 0
+        double sd[4 * NRP + 2];         // dv_r/dy_a, -, dv_r/dy_b, -; [4*NRP] = 0
+        double c[NRP];                  // sf_r * p[k_r] of the running solve (0 for the padding reactions)
+        double dump[2];                 // store target of the lanes that own no Jacobian row
+        double y[NS + 2];               // state broadcast; y[NS] = 1
+        double p[Net::NP];              // parameter vector of the running solve (overrides applied)
+        double pb[Net::NP];             // parameter vector of the evaluation (params[mask] = 10**Y)
+        unsigned long long n_solves, n_steps;
     };
 
-    // rates (and optionally their derivatives) from sh.y; all lanes of the group
-    static __device__ __forceinline__ void rates(Shared &sh, int lane, unsigned gmask, bool deriv) {
-        for (int r = lane; r < NR; r += GL) {
-            const int a = Net::rx_a(r), b = Net::rx_b(r);
-            const double c = Net::rx_sf(r) * sh.p[Net::rx_k(r)];
-            const double ya = sh.y[a];
-            if (b < 0) {
-                sh.v[r] = c * ya;
-                if (deriv) { sh.da[r] = c; sh.db[r] = 0.0; }
-            } else {
-                const double yb = sh.y[b];
-                sh.v[r] = c * ya * yb;
-                if (deriv) {
-                    if (a == b) { sh.da[r] = 2.0 * c * ya; sh.db[r] = 0.0; }
-                    else { sh.da[r] = c * yb; sh.db[r] = c * ya; }
-                }
+    static __device__ __forceinline__ void load_tables(Tables &T) {         // whole block
+        for (int i = threadIdx.x; i < NRP; i += blockDim.x) T.rtab[i] = Net::rtab(i);
+        for (int i = threadIdx.x; i < Net::EJ * GL; i += blockDim.x) T.jtab[i] = Net::jtab(i);
+        for (int i = threadIdx.x; i < Net::EJ2 * NXA; i += blockDim.x) T.jtab2[i] = Net::jtab2(i);
+        for (int i = threadIdx.x; i < Net::EF * GL; i += blockDim.x) T.ftab[i] = Net::ftab(i);
+        for (int i = threadIdx.x; i < Net::EF2 * NXA; i += blockDim.x) T.ftab2[i] = Net::ftab2(i);
+    }
+    static __device__ __forceinline__ void init_shared(Shared &sh, int lane, unsigned gmask) {   // one group
+        for (int i = lane; i < NS * LD; i += GL) sh.J[i] = 0.0;
+        if (lane == 0) {
+            sh.sv[2 * NRP] = sh.sv[2 * NRP + 1] = 0.0;
+            sh.sd[4 * NRP] = sh.sd[4 * NRP + 1] = 0.0;
+            sh.y[NS] = 1.0;
+            sh.y[NS + 1] = 0.0;
+            sh.n_solves = sh.n_steps = 0ull;
+        }
+        __syncwarp(gmask);
+    }
+
+    static __device__ __forceinline__ void rate_constants(Shared &sh, int lane, unsigned gmask) {
+        __syncwarp(gmask);
+        for (int r = lane; r < NRP; r += GL) sh.c[r] = r < NR ? Net::rx_sf(r) * sh.p[Net::rx_k(r)] : 0.0;
+        __syncwarp(gmask);
+    }
+
+    // rates (and their derivatives) from sh.y into the signed value tables; all lanes of the group
+    template <bool DERIV>
+    static __device__ __forceinline__ void rates(Shared &sh, const Tables &T, int lane, unsigned gmask) {
+#pragma unroll
+        for (int m = 0; m < NRM; ++m) {
+            const int r = m * GL + lane;
+            const unsigned int t = T.rtab[r];
+            const double c = sh.c[r], ya = sh.y[t & 0xffffu], yb = sh.y[t >> 16];
+            const double cy = c * yb, v = cy * ya;
+            *reinterpret_cast<double2 *>(&sh.sv[2 * r]) = make_double2(v, -v);
+            if (DERIV) {
+                const double db = c * ya;
+                *reinterpret_cast<double2 *>(&sh.sd[4 * r]) = make_double2(cy, -cy);
+                *reinterpret_cast<double2 *>(&sh.sd[4 * r + 2]) = make_double2(db, -db);
             }
         }
         __syncwarp(gmask);
     }
 
-    // f_i at the state held in sh.y (rates must be current)
-    static __device__ __forceinline__ double rhs_row(const Shared &sh, int lane) {
-        double f = 0.0;
-        if (lane < NS)
-            for (int z = Net::row_ptr(lane); z < Net::row_ptr(lane + 1); ++z)
-                f = fma((double)Net::row_coef(z), sh.v[Net::row_rx(z)], f);
-        return f;
+    // f of this lane's core / leaf species at the state the rates were evaluated at
+    static __device__ __forceinline__ void rhs_rows(const Shared &sh, const Tables &T, int lane, double &f, double &f2) {
+        double fa = 0.0, fb = 0.0;
+#pragma unroll
+        for (int e = 0; e < Net::EF; ++e) {
+            const double t = sh.sv[T.ftab[e * GL + lane]];
+            if (e & 1) fb += t;
+            else fa += t;
+        }
+        f = fa + fb;
+        f2 = 0.0;
+        if (NX > 0 && lane < NX) {
+#pragma unroll
+            for (int e = 0; e < Net::EF2; ++e) f2 += sh.sv[T.ftab2[e * NXA + lane]];
+        }
     }
 
-    static __device__ __forceinline__ void publish(Shared &sh, int lane, unsigned gmask, double yi) {
+    static __device__ __forceinline__ void publish(Shared &sh, int lane, unsigned gmask, double yi, double y2) {
         __syncwarp(gmask);
-        if (lane < NS) sh.y[lane] = yi;
+        if (lane < NC) sh.y[lane] = yi;
+        if (NX > 0 && lane < NX) sh.y[NC + lane] = y2;
         __syncwarp(gmask);
     }
 
-    // One Kaps-Rentrop step for the whole group.  yi = this lane's species; returns false on a bad pivot.
-    static __device__ bool step(Shared &sh, int lane, unsigned gmask, int gbase, double yi, double h, double &ynew,
-                                double &yerr) {
+    // structural nonzeros of this lane's Jacobian rows (derivative table must be current); branch-free
+    static __device__ __forceinline__ void jac_rows(Shared &sh, const Tables &T, int lane) {
+        double acc = 0.0;
+        double *row = lane < NC ? sh.J + lane * LD : sh.dump;
+#pragma unroll
+        for (int e = 0; e < Net::EJ; ++e) {
+            const unsigned int t = T.jtab[e * GL + lane];
+            acc = sh.sd[t & 0xffffu] + ((t >> 24) ? 0.0 : acc);
+            row[(t >> 16) & 0xffu] = acc;
+        }
+        if (NX > 0 && lane < NX) {
+            acc = 0.0;
+            row = sh.J + (NC + lane) * LD;
+#pragma unroll
+            for (int e = 0; e < Net::EJ2; ++e) {
+                const unsigned int t = T.jtab2[e * NXA + lane];
+                acc = sh.sd[t & 0xffffu] + ((t >> 24) ? 0.0 : acc);
+                row[(t >> 16) & 0xffu] = acc;
+            }
+        }
+    }
+
+    // One Kaps-Rentrop step for the whole group.  (yi, y2) = this lane's core / leaf species;
+    // returns false on a bad pivot.
+    static __device__ bool step(Shared &sh, const Tables &T, int lane, unsigned gmask, int gbase, double yi, double y2,
+                                double h, double &ynew, double &ynew2, double &yerr, double &yerr2) {
         constexpr double GAM = 0.5, A21 = 2.0, A31 = 48.0 / 25.0, A32 = 6.0 / 25.0;
         constexpr double C21 = -8.0, C31 = 372.0 / 25.0, C32 = 12.0 / 5.0, C41 = -112.0 / 125.0,
                          C42 = -54.0 / 125.0, C43 = -2.0 / 5.0;
         constexpr double B1 = 19.0 / 9.0, B2 = 0.5, B3 = 25.0 / 108.0, B4 = 125.0 / 108.0;
         constexpr double E1 = 17.0 / 54.0, E2 = 7.0 / 36.0, E4 = 125.0 / 108.0;
         const double ih = 1.0 / h, diag = 1.0 / (GAM * h);
-        // ---- Jacobian rows into shared memory, then M row into registers ----------------------
-        publish(sh, lane, gmask, yi);
-        rates(sh, lane, gmask, true);
-        if (lane < NS) {
+        // ---- Jacobian rows into shared memory, then the core row of M into registers ----------
+        publish(sh, lane, gmask, yi, y2);
+        rates<true>(sh, T, lane, gmask);
+        jac_rows(sh, T, lane);
+        double f0, f02;
+        rhs_rows(sh, T, lane, f0, f02);
+        __syncwarp(gmask);
+        double M[NC], A[NXA];
+        {
+            // M = diag*I - J: the diagonal is folded in through shared memory (a per-lane select over the
+            // register row makes the compiler spill the row and index it dynamically)
+            double *row = sh.J + (lane < NC ? lane : 0) * LD;                // rows are 16-byte aligned (LD even)
+            const double jd = row[lane < NC ? lane : 0];
+            if (lane < NC) row[lane] = jd - diag;
 #pragma unroll
-            for (int q = 0; q < NS; ++q) sh.J[lane][q] = 0.0;
-            for (int z = Net::row_ptr(lane); z < Net::row_ptr(lane + 1); ++z) {
-                const int r = Net::row_rx(z);
-                const double coef = (double)Net::row_coef(z);
-                sh.J[lane][Net::rx_a(r)] += coef * sh.da[r];
-                if (Net::rx_b(r) >= 0 && Net::rx_b(r) != Net::rx_a(r)) sh.J[lane][Net::rx_b(r)] += coef * sh.db[r];
+            for (int q = 0; q + 1 < NC; q += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(row + q);
+                M[q] = -t.x;
+                M[q + 1] = -t.y;
+            }
+            if (NC & 1) M[NC - 1] = -row[NC - 1];
+#pragma unroll
+            for (int l = 0; l < NXA; ++l) A[l] = l < NX ? -row[NC + l] : 0.0;
+            if (lane < NC) row[lane] = jd;
+            if (GL > NC) {                                                   // lanes without a row: zero, so they never contribute
+                const bool core = lane < NC;
+#pragma unroll
+                for (int q = 0; q < NC; ++q) M[q] = core ? M[q] : 0.0;
+#pragma unroll
+                for (int l = 0; l < NXA; ++l) A[l] = core ? A[l] : 0.0;
             }
         }
-        const double f0 = rhs_row(sh, lane);
-        double M[NS];
-#pragma unroll
-        for (int q = 0; q < NS; ++q) M[q] = lane < NS ? (q == lane ? diag : 0.0) - sh.J[lane][q] : (q == lane ? 1.0 : 0.0);
-        // ---- LU without pivoting over shuffles: after column c, rows > c hold l_rc in M[c] ----
-        bool ok = true;
-#pragma unroll
-        for (int c = 0; c < NS; ++c) {
-            const double piv = __shfl_sync(gmask, M[c], gbase + c);
-            ok = ok && (fabs(piv) > 1e-300) && (piv == piv);
-            const double l = M[c] * (1.0 / piv);
-            if (lane > c) M[c] = l;
-#pragma unroll
-            for (int q = c + 1; q < NS; ++q) {
-                const double pq = __shfl_sync(gmask, M[q], gbase + c);
-                if (lane > c) M[q] = fma(-l, pq, M[q]);
-            }
-        }
+        double inv_d = 1.0, inv_d2 = 0.0;
+        const bool ok = Net::lu(M, A, sh.J, diag, lane, gmask, gbase, inv_d, inv_d2);
         if (!__all_sync(gmask, ok)) return false;
-        double dsel = 1.0;                                // M[lane] with static indexing (keeps M in registers)
-#pragma unroll
-        for (int q = 0; q < NS; ++q) dsel = q == lane ? M[q] : dsel;
-        const double inv_d = 1.0 / dsel;
-        auto solve = [&](double b) -> double {
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {              // forward: L has unit diagonal
-                const double bc = __shfl_sync(gmask, b, gbase + c);
-                if (lane > c && lane < NS) b = fma(-M[c], bc, b);
+        // ---- stages: one rolled loop, so the generated substitution code exists once per kernel (the
+        // four inlined copies made a step ~30 k instructions long and thrashed the instruction cache) ----
+        double g1 = 0.0, g2 = 0.0, g3 = 0.0, g4 = 0.0, g12 = 0.0, g22 = 0.0, g32 = 0.0, g42 = 0.0;
+        double f3 = 0.0, f32 = 0.0;
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            double b, b2;
+            if (stage == 0) {
+                b = f0;
+                b2 = f02;
+            } else if (stage == 3) {
+                b = fma(C43 * ih, g3, fma(C42 * ih, g2, fma(C41 * ih, g1, f3)));
+                b2 = fma(C43 * ih, g32, fma(C42 * ih, g22, fma(C41 * ih, g12, f32)));
+            } else {
+                if (stage == 1) publish(sh, lane, gmask, fma(A21, g1, yi), fma(A21, g12, y2));
+                else publish(sh, lane, gmask, fma(A32, g2, fma(A31, g1, yi)), fma(A32, g22, fma(A31, g12, y2)));
+                rates<false>(sh, T, lane, gmask);
+                rhs_rows(sh, T, lane, f3, f32);
+                if (stage == 1) {
+                    b = fma(C21 * ih, g1, f3);
+                    b2 = fma(C21 * ih, g12, f32);
+                } else {
+                    b = fma(C32 * ih, g2, fma(C31 * ih, g1, f3));
+                    b2 = fma(C32 * ih, g22, fma(C31 * ih, g12, f32));
+                }
             }
-#pragma unroll
-            for (int c = NS - 1; c >= 0; --c) {         // backward
-                if (lane == c) b *= inv_d;
-                const double bc = __shfl_sync(gmask, b, gbase + c);
-                if (lane < c) b = fma(-M[c], bc, b);
-            }
-            return b;
-        };
-        // ---- stages -----------------------------------------------------------------------------
-        const double g1 = solve(f0);
-        publish(sh, lane, gmask, fma(A21, g1, yi));
-        rates(sh, lane, gmask, false);
-        const double g2 = solve(fma(C21 * ih, g1, rhs_row(sh, lane)));
-        publish(sh, lane, gmask, fma(A32, g2, fma(A31, g1, yi)));
-        rates(sh, lane, gmask, false);
-        const double f3 = rhs_row(sh, lane);
-        const double g3 = solve(fma(C32 * ih, g2, fma(C31 * ih, g1, f3)));
-        const double g4 = solve(fma(C43 * ih, g3, fma(C42 * ih, g2, fma(C41 * ih, g1, f3))));
+            Net::solve(M, A, sh.J, inv_d, inv_d2, b, b2, lane, gmask, gbase);
+            if (stage == 0) { g1 = b; g12 = b2; }
+            else if (stage == 1) { g2 = b; g22 = b2; }
+            else if (stage == 2) { g3 = b; g32 = b2; }
+            else { g4 = b; g42 = b2; }
+        }
         ynew = yi + B1 * g1 + B2 * g2 + B3 * g3 + B4 * g4;
         yerr = E1 * g1 + E2 * g2 + E4 * g4;
+        ynew2 = y2 + B1 * g12 + B2 * g22 + B3 * g32 + B4 * g42;
+        yerr2 = E1 * g12 + E2 * g22 + E4 * g42;
         return true;
     }
 
-    // Log-likelihood of the system whose parameters are in sh.p (group-uniform result).
-    static __device__ double solve_loglike(Shared &sh, const double *B, int lane, unsigned gmask, int gbase) {
-        const int nt = (int)B[OB_NTIMES], like = (int)B[OB_LIKE], max_steps = (int)B[OB_MAXSTEPS];
-        const int nrows = (int)B[OB_NROWS];
-        const double rtol = B[OB_RTOL], atol = B[OB_ATOL];
-        const double *tspan = B + (int)B[OB_OFF_TSPAN], *obsidx = B + (int)B[OB_OFF_OBSIDX];
-        const double *data = B + (int)B[OB_OFF_DATA], *sd = B + (int)B[OB_OFF_SD], *mask = B + (int)B[OB_OFF_MASK];
-        double yi = 0.0;
-        if (lane < NS) yi = Net::init_kind(lane) ? sh.p[Net::init_par(lane)] : Net::init_val(lane);
+    struct Control {
+        double rtol, atol, h;
+        int steps, max_steps;
+    };
+
+    // Integrate from t to tn (adaptive steps, the last one clipped to land on tn); group-uniform verdict.
+    static __device__ bool advance(Shared &sh, const Tables &T, int lane, unsigned gmask, int gbase, double &yi,
+                                   double &y2, double &t, double tn, Control &ctl) {
+        double h = ctl.h;
+        while (t < tn) {                             // every quantity below is group-uniform
+            const double rem = tn - t;
+            const bool last = h >= rem;
+            const double hh = last ? rem : h;
+            if (++ctl.steps > ctl.max_steps) return false;
+            double ynew, ynew2, yerr, yerr2;
+            if (!step(sh, T, lane, gmask, gbase, yi, y2, hh, ynew, ynew2, yerr, yerr2)) {
+                if (hh < 1e-300) return false;
+                h = hh * 0.1;
+                continue;
+            }
+            double e = 0.0;
+            bool fin = true;
+            if (lane < NC) {
+                e = fabs(yerr) / (ctl.atol + ctl.rtol * fmax(fabs(yi), fabs(ynew)));
+                fin = isfinite(ynew) && e == e;
+            }
+            if (NX > 0 && lane < NX) {
+                const double e2 = fabs(yerr2) / (ctl.atol + ctl.rtol * fmax(fabs(y2), fabs(ynew2)));
+                fin = fin && isfinite(ynew2) && e2 == e2;
+                e = fmax(e, e2);
+            }
+#pragma unroll
+            for (int o = GL / 2; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(gmask, e, o));
+            fin = __all_sync(gmask, fin);
+            if (!fin) {
+                if (hh < 1e-300) return false;
+                h = hh * 0.1;
+                continue;
+            }
+            const double fac = e > 0.0 ? fmin(5.0, fmax(0.2, 0.9 * pow(e, -0.25))) : 5.0;
+            if (e <= 1.0) {
+                yi = ynew;
+                y2 = ynew2;
+                t = last ? tn : t + hh;
+                // a step clipped to land on an output time only lowers the running step size if its
+                // own error asks for that; otherwise the unclipped proposal stands
+                if (!last || fac < 1.0) h = hh * fac;
+                else h = fmax(h, hh * fac);
+            } else {
+                h = hh * fac;
+                if (h < 1e-14 * fabs(tn)) return false;
+            }
+        }
+        ctl.h = h;
+        return true;
+    }
+
+    // sh.p = sh.pb with the overrides of condition c; optionally the pre-equilibration zeros
+    static __device__ __forceinline__ void condition_params(Shared &sh, const double *B, int c, bool zeroed, int lane,
+                                                            unsigned gmask) {
+        const int np = (int)B[PB_NPARAMS];
+        const double *optr = B + (int)B[PB_OFF_OVERPTR], *oidx = B + (int)B[PB_OFF_OVERIDX];
+        const double *oval = B + (int)B[PB_OFF_OVERVAL], *zidx = B + (int)B[PB_OFF_ZEROIDX];
+        __syncwarp(gmask);
+        for (int i = lane; i < np; i += GL) sh.p[i] = sh.pb[i];
+        __syncwarp(gmask);
+        for (int z = (int)optr[c] + lane; z < (int)optr[c + 1]; z += GL) sh.p[(int)oidx[z]] = oval[z];
+        __syncwarp(gmask);
+        if (zeroed)
+            for (int z = lane; z < (int)B[PB_NZERO]; z += GL) sh.p[(int)zidx[z]] = 0.0;
+        rate_constants(sh, lane, gmask);
+    }
+
+    // Contribution of condition c to the log-likelihood for the parameters in sh.pb (group-uniform):
+    // pre-equilibration, main solve, data rows.  -inf on integrator failure.
+    static __device__ double condition_loglike(Shared &sh, const Tables &T, const double *B, int c, int lane,
+                                               unsigned gmask, int gbase) {
+        const int nt = (int)B[PB_NTIMES], like = (int)B[PB_LIKE];
+        const double *tspan = B + (int)B[PB_OFF_TSPAN], *meta = B + (int)B[PB_OFF_ROWMETA];
+        const double *data = B + (int)B[PB_OFF_DATA], *sd = B + (int)B[PB_OFF_SD], *mask = B + (int)B[PB_OFF_MASK];
+        const double *cterm = B + (int)B[PB_OFF_CTERM], *rowptr = B + (int)B[PB_OFF_ROWPTR];
+        const double *stopptr = B + (int)B[PB_OFF_STOPPTR], *stops = B + (int)B[PB_OFF_STOPS];
+        const int r0 = (int)rowptr[c], r1 = (int)rowptr[c + 1];
+        const int s0 = (int)stopptr[c], s1 = (int)stopptr[c + 1];
+        Control ctl;
+        ctl.rtol = B[PB_RTOL];
+        ctl.atol = B[PB_ATOL];
+        ctl.steps = 0;
+        ctl.max_steps = (int)B[PB_MAXSTEPS];
+        const bool preeq = B[PB_PREEQ] != 0.0;
+        condition_params(sh, B, c, preeq, lane, gmask);
+        double yi = 0.0, y2 = 0.0;
+        if (lane < NC) yi = Net::init_kind(lane) ? sh.p[Net::init_par(lane)] : Net::init_val(lane);
+        if (NX > 0 && lane < NX) y2 = Net::init_kind(NC + lane) ? sh.p[Net::init_par(NC + lane)] : Net::init_val(NC + lane);
+        bool failed = false;
+        if (preeq) {
+            const double te = B[PB_PREEQ_TEND];
+            double t = 0.0;
+            ctl.h = 1e-3 * te;
+            failed = !advance(sh, T, lane, gmask, gbase, yi, y2, t, te, ctl);
+            if (lane == 0) sh.n_solves += 1;
+            if (!failed && B[PB_PREEQ_TOL] >= 0.0) {        // equilibrium test: max |dy/dt| at t_end
+                publish(sh, lane, gmask, yi, y2);
+                rates<false>(sh, T, lane, gmask);
+                double f, f2;
+                rhs_rows(sh, T, lane, f, f2);
+                double e = fmax(fabs(f), fabs(f2));
+                if (e != e) e = INFINITY;
+#pragma unroll
+                for (int o = GL / 2; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(gmask, e, o));
+                failed = !(e <= B[PB_PREEQ_TOL]);
+            }
+            if (!failed) condition_params(sh, B, c, false, lane, gmask);
+        }
         double acc = 0.0;
-        auto misfit = [&](int it) {                      // lane 0 accumulates; sh.y must hold the state
-            publish(sh, lane, gmask, yi);
+        auto misfit = [&](int it) {                      // lane 0 accumulates
+            publish(sh, lane, gmask, yi, y2);
             if (lane == 0) {
-                for (int r = 0; r < nrows; ++r) {
+                for (int r = r0; r < r1; ++r) {
                     if (mask[r * nt + it] == 0.0) continue;
-                    const int o = (int)obsidx[r];
+                    const int o = (int)meta[4 * r + 1];
                     double sim = 0.0;
                     for (int z = Net::obs_ptr(o); z < Net::obs_ptr(o + 1); ++z) sim = fma(Net::obs_coef(z), sh.y[Net::obs_sp(z)], sim);
+                    sim = sim / meta[4 * r + 2];
                     const double mu = data[r * nt + it];
                     if (like == ODE_SNLPDF) {
-                        const double s = sd[r * nt + it], z2 = (sim - mu) / s;
-                        acc += -0.5 * z2 * z2 - log(s) - GL_HALF_LOG_2PI;
+                        const double zz = (sim - mu) / sd[r * nt + it];
+                        if ((int)meta[4 * r + 3] == ODE_ROW_HALFNORM && !(zz >= 0.0)) acc = zz == zz ? -INFINITY : zz;
+                        else acc += fma(-0.5 * zz, zz, cterm[r * nt + it]);
                     } else {
                         const double e = mu - sim;
                         acc -= like == ODE_SSE ? e * e : e * e * sd[r * nt + it];
@@ -179,108 +415,150 @@ struct CoopOde {
                 }
             }
         };
-        misfit(0);
-        double t = tspan[0];
-        double h = fmin(1e-3 * (tspan[nt - 1] - tspan[0]), tspan[1] - tspan[0]);
-        int steps = 0;
-        bool failed = false;
-        for (int it = 1; it < nt && !failed; ++it) {
-            const double tn = tspan[it];
-            while (t < tn) {                             // every quantity below is group-uniform
-                const double rem = tn - t;
-                const bool last = h >= rem;
-                const double hh = last ? rem : h;
-                if (++steps > max_steps) { failed = true; break; }
-                double ynew, yerr;
-                if (!step(sh, lane, gmask, gbase, yi, hh, ynew, yerr)) {
-                    if (hh < 1e-300) { failed = true; break; }
-                    h = hh * 0.1;
-                    continue;
-                }
-                double e = 0.0;
-                bool fin = true;
-                if (lane < NS) {
-                    e = fabs(yerr) / (atol + rtol * fmax(fabs(yi), fabs(ynew)));
-                    fin = isfinite(ynew) && e == e;
-                }
-#pragma unroll
-                for (int o = GL / 2; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(gmask, e, o));
-                fin = __all_sync(gmask, fin);
-                if (!fin) {
-                    if (hh < 1e-300) { failed = true; break; }
-                    h = hh * 0.1;
-                    continue;
-                }
-                const double fac = e > 0.0 ? fmin(5.0, fmax(0.2, 0.9 * pow(e, -0.25))) : 5.0;
-                if (e <= 1.0) {
-                    yi = ynew;
-                    t = last ? tn : t + hh;
-                    if (!last || fac < 1.0) h = hh * fac;
-                    else h = fmax(h, hh * fac);
-                } else {
-                    h = hh * fac;
-                    if (h < 1e-14 * fabs(tn)) { failed = true; break; }
-                }
+        if (!failed && s1 > s0) {
+            double t = tspan[0];
+            const double t_end = tspan[(int)stops[s1 - 1]];
+            int s = s0;
+            if ((int)stops[s] == 0) { misfit(0); ++s; }
+            if (s < s1) {
+                ctl.h = fmin(1e-3 * (t_end - t), tspan[(int)stops[s]] - t);
+                if (lane == 0) sh.n_solves += 1;
             }
-            if (!failed) misfit(it);
+            for (; s < s1 && !failed; ++s) {
+                const int it = (int)stops[s];
+                failed = !advance(sh, T, lane, gmask, gbase, yi, y2, t, tspan[it], ctl);
+                if (!failed) misfit(it);
+            }
         }
+        if (lane == 0) sh.n_steps += (unsigned long long)ctl.steps;
         acc = __shfl_sync(gmask, acc, gbase);
         return (failed || acc != acc) ? -INFINITY : acc;
     }
 
-    // params[mask] = 10**Y with component jrep of Y replaced by v (jrep < 0: none); Y in shared memory
+    // sum of norm(loc, scale).logpdf over the cycle products of sh.pb (run_jarm_multinest.py:72-103)
+    static __device__ double cycle_logp(const Shared &sh, const double *B) {
+        const int nc = (int)B[PB_NCYCLES];
+        if (nc == 0) return 0.0;
+        const double *ptr = B + (int)B[PB_OFF_CYCPTR], *fac = B + (int)B[PB_OFF_CYCFAC];
+        const double loc = B[PB_CYC_LOC], scale = B[PB_CYC_SCALE];
+        double lp = 0.0;
+        for (int i = 0; i < nc; ++i) {
+            double box = 1.0;
+            for (int z = (int)ptr[i]; z < (int)ptr[i + 1]; ++z) {
+                const double t = sh.pb[(int)fac[3 * z]] / sh.pb[(int)fac[3 * z + 1]];
+                box = box * (fac[3 * z + 2] != 0.0 ? 1.0 / t : t);
+            }
+            const double zz = (box - loc) / scale;
+            lp += -0.5 * zz * zz - log(scale) - GL_HALF_LOG_2PI;
+        }
+        return lp != lp ? -INFINITY : lp;
+    }
+
+    // pb[mask] = 10**Y with component jrep of Y replaced by v (jrep < 0: none)
     static __device__ __forceinline__ void load_params(Shared &sh, const double *B, const double *Y, int stride, int d,
                                                        int jrep, double v, int lane, unsigned gmask) {
-        const int np = (int)B[OB_NPARAMS];
-        const double *nominal = B + (int)B[OB_OFF_NOMINAL], *map = B + (int)B[OB_OFF_MAP];
-        const double *islog = B + (int)B[OB_OFF_ISLOG];
+        const int np = (int)B[PB_NPARAMS];
+        const double *nominal = B + (int)B[PB_OFF_NOMINAL], *map = B + (int)B[PB_OFF_MAP];
+        const double *islog = B + (int)B[PB_OFF_ISLOG];
         __syncwarp(gmask);
-        for (int i = lane; i < np; i += GL) sh.p[i] = nominal[i];
+        for (int i = lane; i < np; i += GL) sh.pb[i] = nominal[i];
         __syncwarp(gmask);
         for (int j = lane; j < d; j += GL) {
             const double yj = j == jrep ? v : Y[j * stride];
-            sh.p[(int)map[j]] = islog[j] != 0.0 ? exp10(yj) : yj;
+            sh.pb[(int)map[j]] = islog[j] != 0.0 ? exp10(yj) : yj;
         }
         __syncwarp(gmask);
     }
+
+    // conditions sub, sub + nsub, ... of the evaluation whose parameters are in sh.pb; subset 0 adds the cycle terms
+    static __device__ double subset_loglike(Shared &sh, const Tables &T, const double *B, int sub, int nsub, int lane,
+                                            unsigned gmask, int gbase) {
+        const int ncond = (int)B[PB_NCOND];
+        double total = 0.0;
+        if (sub == 0) {
+            double lp = 0.0;
+            if (lane == 0) lp = cycle_logp(sh, B);
+            total = __shfl_sync(gmask, lp, gbase);
+        }
+        for (int c = sub; c < ncond; c += nsub) {
+            if (total == -INFINITY) break;                                   // nothing can lift it
+            total += condition_loglike(sh, T, B, c, lane, gmask, gbase);
+        }
+        return total != total ? -INFINITY : total;
+    }
 };
+
+// device-resident counters of one plugin (allocated on first use, never freed)
+template <class Net>
+inline CoopCounters *coop_counter_store() {
+    static CoopCounters *p = nullptr;
+    if (!p) {
+        if (cudaMalloc(&p, sizeof(CoopCounters)) != cudaSuccess) { p = nullptr; return nullptr; }
+        cudaMemset(p, 0, sizeof(CoopCounters));
+    }
+    return p;
+}
 
 // ---- batch evaluation: one group per parameter set ------------------------------------------------
 template <class Net>
-__global__ void __launch_bounds__(128) ode_coop_eval_kernel(ModelDev M, const double *__restrict__ x, long long n,
-                                                            double *__restrict__ out) {
+__global__ void __launch_bounds__(128, GL_COOP_MIN_BLOCKS) ode_coop_eval_kernel(ModelDev M, const double *__restrict__ x, long long n,
+                                                            double *__restrict__ out, CoopCounters *ctr,
+                                                            unsigned long long *next) {
     using C = CoopOde<Net>;
     constexpr int GL = Net::GL, GPB = 128 / GL;
-    __shared__ typename C::Shared sh[GPB];
+    extern __shared__ double2 dyn2[];
+    typename C::Tables &T = *reinterpret_cast<typename C::Tables *>(dyn2);
+    typename C::Shared *shs = reinterpret_cast<typename C::Shared *>(&T + 1);
     const int g = threadIdx.x / GL, lane = threadIdx.x % GL;
     const int gbase = (threadIdx.x & 31) / GL * GL;
     const unsigned gmask = (GL == 32 ? 0xffffffffu : ((1u << GL) - 1u)) << gbase;
-    for (long long i = (long long)blockIdx.x * GPB + g; i < n; i += (long long)gridDim.x * GPB) {
-        C::load_params(sh[g], M.aux0, x + i * M.d, 1, M.d, -1, 0.0, lane, gmask);
-        const double L = C::solve_loglike(sh[g], M.aux0, lane, gmask, gbase);
+    typename C::Shared &sh = shs[g];
+    C::load_tables(T);
+    C::init_shared(sh, lane, gmask);
+    __syncthreads();
+    unsigned long long evals = 0ull;
+    // solves differ in length by orders of magnitude: groups claim parameter sets one at a time
+    for (;;) {
+        long long i = 0;
+        if (lane == 0) i = (long long)atomicAdd(next, 1ull);
+        i = __shfl_sync(gmask, i, gbase);
+        if (i >= n) break;
+        C::load_params(sh, M.aux0, x + i * M.d, 1, M.d, -1, 0.0, lane, gmask);
+        const double L = C::subset_loglike(sh, T, M.aux0, 0, 1, lane, gmask, gbase);
         if (lane == 0) out[i] = L;
+        ++evals;
+    }
+    if (lane == 0 && evals) {
+        atomicAdd(&ctr->evals, evals);
+        atomicAdd(&ctr->solves, sh.n_solves);
+        atomicAdd(&ctr->steps, sh.n_steps);
     }
 }
 
 
 // ---- walkers with a cooperative likelihood ---------------------------------------------------------
 // Same chain as walk_kernel (walker.cuh) -- same Philox counters, proposal, prior test, hard wall,
-// phases and pooled width adaptation -- but the GL lanes of a group evaluate ONE trial move together
-// instead of speculating on GL different ones.
+// phases and pooled width adaptation -- but the lanes of a group integrate ONE system together
+// instead of speculating on different trial moves, and a walker owns `gpw` groups, one per subset of
+// the protocol's conditions (independent solves), whose partial sums meet in shared memory.
 template <class Net>
-__global__ void __launch_bounds__(128) walk_coop_kernel(WalkParams P, ModelDev M, int phase) {
+__global__ void __launch_bounds__(128, GL_COOP_MIN_BLOCKS) walk_coop_kernel(WalkParams P, ModelDev M, int phase, int gpw,
+                                                        CoopCounters *ctr) {
     using C = CoopOde<Net>;
-    constexpr int GL = Net::GL, WPB = 128 / GL;
-    __shared__ typename C::Shared sh[WPB];
-    extern __shared__ double dyn[];
+    constexpr int GL = Net::GL, GPB = 128 / GL;
+    extern __shared__ double2 dyn2[];
     EngineState *S = P.S;
     if (!S->do_walk) return;
     const int k = S->k_cur, d = P.d;
+    const int WPB = GPB / gpw;                     // walkers per block
     if (blockIdx.x * WPB >= k) return;
-    double *xs = dyn;                              // [d][WPB]
+    typename C::Tables &T = *reinterpret_cast<typename C::Tables *>(dyn2);
+    typename C::Shared *shs = reinterpret_cast<typename C::Shared *>(&T + 1);
+    double *xs = reinterpret_cast<double *>(shs + GPB);   // [d][WPB]
     double *wj = xs + (size_t)d * WPB;
     double *p0s = wj + d, *p1s = p0s + d;
-    int *kinds = reinterpret_cast<int *>(p1s + d);
+    double *part = p1s + d;                        // [2][GPB] partial sums, double-buffered by move parity
+    int *kinds = reinterpret_cast<int *>(part + 2 * GPB);
     unsigned int *acc = reinterpret_cast<unsigned int *>(kinds + d);
     const int tid = threadIdx.x;
     const bool tuning = phase < P.tuning_cycles;
@@ -291,68 +569,101 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(WalkParams P, ModelDev M
         kinds[j] = P.priors->kind[j];
         acc[j] = 0u;
     }
+    C::load_tables(T);
     __syncthreads();
-    const int wl = tid / GL, lane = tid % GL;
+    const int g = tid / GL, lane = tid % GL;
+    const int wl = g / gpw, sub = g % gpw;         // walker of this block, condition subset of this group
+    const int wlane = tid - wl * gpw * GL;         // index inside the walker's threads
+    const int wthreads = gpw * GL;
     const int w = blockIdx.x * WPB + wl;
-    const bool active = w < k;
+    const bool active = wl < WPB && w < k;
     const int gbase = (tid & 31) / GL * GL;
     const unsigned gmask = (GL == 32 ? 0xffffffffu : ((1u << GL) - 1u)) << gbase;
+    // barrier over the threads of one walker: a warp-level sync when they share a warp
+    const unsigned wmask = wthreads >= 32 ? 0xffffffffu : ((1u << wthreads) - 1u) << ((tid & 31) / wthreads * wthreads);
+    auto walker_sync = [&]() {
+        if (wthreads <= 32) __syncwarp(wmask);
+        else asm volatile("barrier.sync %0, %1;" ::"r"(1 + wl), "r"(wthreads) : "memory");   // non-aligned form: the
+        // two groups of a 16-lane pair sharing a warp may arrive from different iterations of their step loops
+    };
+    typename C::Shared &sh = shs[g];
+    C::init_shared(sh, lane, gmask);
+    unsigned long long evals = 0ull;
     double *x = xs + wl;
     const double lstar = S->lstar;
     const uint32_t step = (uint32_t)S->step;
     if (active) {
         const long long slot = P.dead_list[w];
-        const uint32_t g = (uint32_t)(slot + P.row_offset);
+        const uint32_t gid = (uint32_t)(slot + P.row_offset);
         double L;
         if (phase == 0 || !tuning) {
             long long pick = 0;
-            if (lane == 0) {
+            if (wlane == 0) {
                 for (uint32_t a = 0;; ++a) {
-                    const U2 u = philox_uniforms(P.seed, g, step, a, GL_TAG_PICK);
+                    const U2 u = philox_uniforms(P.seed, gid, step, a, GL_TAG_PICK);
                     pick = (long long)(u.a * (double)P.N);
                     if (pick >= P.N) pick = P.N - 1;
                     if (!P.is_dead[pick]) break;
                 }
+                part[g] = __longlong_as_double(pick);
             }
-            pick = __shfl_sync(gmask, pick, gbase);
-            for (int j = lane; j < d; j += GL) x[j * WPB] = P.live[pick * d + j];
+            walker_sync();
+            pick = __double_as_longlong(part[wl * gpw]);
+            walker_sync();
+            for (int j = wlane; j < d; j += wthreads) x[j * WPB] = P.live[pick * d + j];
             L = P.logl[pick];
         } else {
-            for (int j = lane; j < d; j += GL) x[j * WPB] = P.scratch_x[(size_t)w * d + j];
+            for (int j = wlane; j < d; j += wthreads) x[j * WPB] = P.scratch_x[(size_t)w * d + j];
             L = P.scratch_l[w];
         }
-        __syncwarp(gmask);
+        walker_sync();
         const int n_moves = (tuning ? 20 : P.iterations + P.burn_in) * d;
         const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * d);
         const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
+        int parity = 0;
         for (int m = 0; m < n_moves; ++m) {
             const int j = m % d;
-            const U2 ru = philox_uniforms(P.seed, g, step, c2_base + (uint32_t)m, GL_TAG_MOVE);
+            const U2 ru = philox_uniforms(P.seed, gid, step, c2_base + (uint32_t)m, GL_TAG_MOVE);
             const double width = wj[j], xj = x[j * WPB];
             const double stepv = __dmul_rn(normal ? normcdfinv(ru.a) : ru.a, width);
             const double nj = __dadd_rn(stepv, normal ? xj : __dadd_rn(xj, -0.5 * width));
-            if (prior_accept(kinds[j], p0s[j], p1s[j], xj, nj, ru.b)) {        // group-uniform
-                C::load_params(sh[wl], M.aux0, x, WPB, d, j, nj, lane, gmask);
-                const double Lt = C::solve_loglike(sh[wl], M.aux0, lane, gmask, gbase);
+            if (prior_accept(kinds[j], p0s[j], p1s[j], xj, nj, ru.b)) {        // walker-uniform
+                C::load_params(sh, M.aux0, x, WPB, d, j, nj, lane, gmask);
+                double Lt = C::subset_loglike(sh, T, M.aux0, sub, gpw, lane, gmask, gbase);
+                ++evals;
+                if (gpw > 1) {
+                    double *pp = part + parity * GPB + wl * gpw;
+                    if (lane == 0) pp[sub] = Lt;
+                    walker_sync();
+                    Lt = pp[0];
+                    for (int s = 1; s < gpw; ++s) Lt += pp[s];
+                    if (Lt != Lt) Lt = -INFINITY;
+                    parity ^= 1;
+                }
                 if (Lt > lstar) {
-                    __syncwarp(gmask);
-                    if (lane == 0) {
+                    walker_sync();
+                    if (wlane == 0) {
                         x[j * WPB] = nj;
                         if (tuning) atomicAdd(&acc[j], 1u);
                     }
                     L = Lt;
-                    __syncwarp(gmask);
+                    walker_sync();
                 }
             }
         }
         if (tuning) {
             if (phase + 1 < P.tuning_cycles) {
-                for (int j = lane; j < d; j += GL) P.scratch_x[(size_t)w * d + j] = x[j * WPB];
-                if (lane == 0) P.scratch_l[w] = L;
+                for (int j = wlane; j < d; j += wthreads) P.scratch_x[(size_t)w * d + j] = x[j * WPB];
+                if (wlane == 0) P.scratch_l[w] = L;
             }
         } else {
-            for (int j = lane; j < d; j += GL) P.live[slot * d + j] = x[j * WPB];
-            if (lane == 0) P.logl[slot] = L;
+            for (int j = wlane; j < d; j += wthreads) P.live[slot * d + j] = x[j * WPB];
+            if (wlane == 0) P.logl[slot] = L;
+        }
+        if (lane == 0) {
+            if (sub == 0) atomicAdd(&ctr->evals, evals);
+            atomicAdd(&ctr->solves, sh.n_solves);
+            atomicAdd(&ctr->steps, sh.n_steps);
         }
     }
     if (tuning) {
@@ -362,26 +673,59 @@ __global__ void __launch_bounds__(128) walk_coop_kernel(WalkParams P, ModelDev M
     }
 }
 
+// groups a walker spreads its conditions over: as many as there are conditions while a block still
+// holds whole walkers (1, 2 or 4 groups of a 128-thread block)
 template <class Net>
-inline int walk_coop_launch(const WalkParams &P, const ModelDev &M, cudaStream_t st) {
-    constexpr int WPB = 128 / Net::GL;
-    const int smem = (int)(sizeof(double) * ((size_t)P.d * WPB + 3 * (size_t)P.d) + 2 * sizeof(int) * P.d + 16);
+inline int coop_groups_per_walker(const ModelDev &M, int ncond) {
+    constexpr int GPB = 128 / Net::GL;
+    int gpw = 1;
+    while (gpw * 2 <= GPB && gpw * 2 <= ncond && ncond % (gpw * 2) == 0) gpw *= 2;
+    return gpw;
+}
+
+template <class Net>
+inline int walk_coop_launch(const WalkParams &P, const ModelDev &M, int ncond, cudaStream_t st) {
+    using C = CoopOde<Net>;
+    constexpr int GPB = 128 / Net::GL;
+    const int gpw = coop_groups_per_walker<Net>(M, ncond);
+    const int WPB = GPB / gpw;
+    const size_t smem = sizeof(typename C::Tables) + sizeof(typename C::Shared) * GPB +
+                        sizeof(double) * ((size_t)P.d * WPB + 3 * (size_t)P.d + 2 * GPB) + 2 * sizeof(int) * P.d + 16;
+    GL_CUDA(cudaFuncSetAttribute(walk_coop_kernel<Net>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CoopCounters *ctr = coop_counter_store<Net>();
+    GL_REQUIRE(ctr != nullptr, "counter allocation failed");
     const int blocks = (P.k_max + WPB - 1) / WPB;
     for (int phase = 0; phase <= P.tuning_cycles; ++phase)
-        walk_coop_kernel<Net><<<blocks, 128, smem, st>>>(P, M, phase);
+        walk_coop_kernel<Net><<<blocks, 128, smem, st>>>(P, M, phase, gpw, ctr);
     GL_CHECK_LAUNCH();
     return GL_OK;
 }
 
 template <class Net>
 inline int ode_coop_eval_launch(const ModelDev &M, const double *x, long long n, double *out, cudaStream_t st) {
+    using C = CoopOde<Net>;
     constexpr int GPB = 128 / Net::GL;
+    const size_t smem = sizeof(typename C::Tables) + sizeof(typename C::Shared) * GPB;
+    GL_CUDA(cudaFuncSetAttribute(ode_coop_eval_kernel<Net>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CoopCounters *ctr = coop_counter_store<Net>();
+    GL_REQUIRE(ctr != nullptr, "counter allocation failed");
     long long blocks = (n + GPB - 1) / GPB;
-    const long long cap = (long long)sm_count() * 8;
+    const long long cap = (long long)sm_count() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    ode_coop_eval_kernel<Net><<<(int)blocks, 128, 0, st>>>(M, x, n, out);
+    GL_CUDA(cudaMemsetAsync(&ctr->next, 0, sizeof(unsigned long long), st));
+    ode_coop_eval_kernel<Net><<<(int)blocks, 128, smem, st>>>(M, x, n, out, ctr, &ctr->next);
     GL_CHECK_LAUNCH();
+    return GL_OK;
+}
+
+template <class Net>
+inline int coop_counters(unsigned long long *out3, int reset) {
+    CoopCounters h, *ctr = coop_counter_store<Net>();
+    GL_REQUIRE(ctr != nullptr, "counter allocation failed");
+    GL_CUDA(cudaMemcpy(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost));
+    out3[0] = h.evals; out3[1] = h.solves; out3[2] = h.steps;
+    if (reset) GL_CUDA(cudaMemset(ctr, 0, 3 * sizeof(unsigned long long)));
     return GL_OK;
 }
 

@@ -32,7 +32,10 @@ enum OdeBlob {
     OB_NROWS = 7, OB_OFF_NOMINAL = 16, OB_OFF_MAP = 17, OB_OFF_ISLOG = 18, OB_OFF_TSPAN = 19, OB_OFF_OBSIDX = 20,
     OB_OFF_DATA = 21, OB_OFF_SD = 22, OB_OFF_MASK = 23, OB_HEADER = 32
 };
+#ifndef GL_ODE_LIKE_TYPES
+#define GL_ODE_LIKE_TYPES
 enum OdeLikeType { ODE_SNLPDF = 0, ODE_MSE = 1, ODE_SSE = 2 };
+#endif
 
 // In-place LU with partial pivoting of an N x N row-major matrix; returns false if singular.
 template <int N>

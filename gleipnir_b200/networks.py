@@ -70,3 +70,126 @@ def jarm_like(n_sites=2):
 
 
 SHIPPED = {"dimerization": dimerization, "model_0": model_0, "jarm_like": jarm_like}
+
+
+# ---- C5: the JARM-shaped network -------------------------------------------------------------
+JARM_N_RATE = 44          # rate constants p[0..43]; p[44..49] are initial amounts
+JARM_CALIBRATED = [1, 5, 9, 11, 15, 17, 19, 23, 25, 27, 31, 35, 36, 37, 38, 39, 41, 43]   # run_jarm_multinest.py:51
+JARM_KCAT = [36, 37]                                                                       # :59
+JARM_ARRESTIN = [44]                                                                       # :56
+JARM_JNK3_INITIALS = [47, 48, 49]                                                          # :58
+JARM_JNK3_TOTAL = 0.6                                                                      # :57
+JARM_NOARRESTIN_JNK3 = [0.592841488, 0.0, 0.007158512]                                     # :111,123
+# evaluate_cycles (run_jarm_multinest.py:72-90): box = product of (p[a]/p[b]) or 1/(p[a]/p[b])
+JARM_CYCLES = [
+    [(21, 20, 0), (23, 22, 0), (1, 0, 1), (5, 4, 1)],
+    [(21, 20, 0), (25, 24, 0), (3, 2, 1), (27, 26, 1)],
+    [(13, 12, 0), (23, 22, 0), (1, 0, 1), (15, 14, 1)],
+    [(7, 6, 0), (25, 24, 0), (3, 2, 1), (11, 10, 1)],
+]
+
+
+def jarm():
+    """SYNTHETIC network of the JARM problem's size and shape.  The reference's C5 script imports
+    `jnk3_no_ask1.model`, `equilibration_function` and `data/exp_data_3min.csv`
+    (examples/pysb_jarm/run_jarm_multinest.py:12-14,24), none of which is in the reference tree
+    (SURVEY 6.3 item 3), so the network below is written to match every index the script uses:
+    50 parameters = 44 rate constants in (kf, kr) pairs + 6 initial amounts; p[36], p[37] the two
+    catalytic constants zeroed during pre-equilibration; p[44] the arrestin amount; p[47..49] the
+    three JNK3 initial amounts; and the four thermodynamic cycles of `evaluate_cycles` (:72-90) are
+    genuine cycles of THIS network (arrestin-kinase, arrestin-JNK3 and the two routes to each
+    ternary complex), so the box products equal 1 for detailed-balance-consistent constants.
+    JNK3 carries two sites (Thr phosphorylated by MKK7, Tyr by MKK4); arrestin scaffolds either
+    kinase, JNK3, or both kinases.  34 species, so the cooperative solver's 32 lanes hold a 32-row
+    core and two leaf species (odegen.py)."""
+    states = ["uu", "pT", "pY", "pp"]
+    sp = ["Arr", "K4", "K7"] + ["J" + s for s in states] + ["Arr_K4", "Arr_K7"] + ["Arr_J" + s for s in states]
+    sp += ["Arr_K4_J" + s for s in states] + ["Arr_K7_J" + s for s in states]
+    sp += ["K4_J" + s for s in states] + ["K7_J" + s for s in states]
+    sp += ["Arr_K4_K7"] + ["Arr_K4_K7_J" + s for s in states]
+    names = [None] * 50
+    vals = [0.0] * 50
+
+    def pair(i, name, kf, kr):
+        names[i], names[i + 1] = "kf_" + name, "kr_" + name
+        vals[i], vals[i + 1] = kf, kr
+
+    pair(0, "Arr_K4", 10.0, 400.0)
+    pair(2, "Arr_K7", 10.0, 100.0)
+    pair(4, "ArrK4_Juu", 10.0, 10.0)
+    pair(6, "Arr_JpY", 10.0, 20.0)
+    pair(8, "Arr_Jpp", 10.0, 100.0)
+    pair(10, "ArrK7_JpY", 10.0, 10.0)
+    pair(12, "Arr_JpT", 10.0, 16.0)
+    pair(14, "ArrK4_JpT", 10.0, 8.0)
+    pair(16, "K4_Juu", 10.0, 60.0)
+    pair(18, "K7_Juu", 10.0, 90.0)
+    pair(20, "Arr_Juu", 10.0, 20.0)
+    pair(22, "ArrJ_K4", 10.0, 200.0)
+    pair(24, "ArrJ_K7", 10.0, 50.0)
+    pair(26, "ArrK7_Juu", 10.0, 10.0)
+    pair(28, "K4_JpT", 10.0, 50.0)
+    pair(30, "K7_JpY", 10.0, 60.0)
+    pair(32, "K4_prod", 10.0, 200.0)
+    pair(34, "K7_prod", 10.0, 200.0)
+    names[36], vals[36] = "kcat_pTyr", 0.5
+    names[37], vals[37] = "kcat_pThr", 0.8
+    pair(38, "ArrK4_prod", 5.0, 100.0)
+    pair(40, "ArrK7_prod", 10.0, 100.0)
+    pair(42, "ArrK4K7_J", 10.0, 15.0)
+    for i, (n, v) in enumerate([("Arr_0", 5.0), ("K4_0", 0.05), ("K7_0", 0.05), ("Juu_0", 0.493), ("JpT_0", 0.0),
+                                ("JpY_0", 0.107)]):
+        names[44 + i], vals[44 + i] = n, v
+    par = dict(zip(names, vals))
+    rx = []
+
+    def bind(a, b, c, i):
+        rx.append((names[i], [a, b], [c]))
+        rx.append((names[i + 1], [c], [a, b]))
+
+    def cat(a, b, i):
+        rx.append((names[i], [a], [b]))
+
+    bind("Arr", "K4", "Arr_K4", 0)
+    bind("Arr", "K7", "Arr_K7", 2)
+    bind("Arr_K7", "K4", "Arr_K4_K7", 0)
+    bind("Arr_K4", "K7", "Arr_K4_K7", 2)
+    bind("Arr", "Juu", "Arr_Juu", 20)
+    bind("Arr", "JpT", "Arr_JpT", 12)
+    bind("Arr", "JpY", "Arr_JpY", 6)
+    bind("Arr", "Jpp", "Arr_Jpp", 8)
+    bind("Arr_K4", "Juu", "Arr_K4_Juu", 4)
+    bind("Arr_K4", "JpT", "Arr_K4_JpT", 14)
+    bind("Arr_K4", "JpY", "Arr_K4_JpY", 38)
+    bind("Arr_K4", "Jpp", "Arr_K4_Jpp", 38)
+    bind("Arr_K7", "Juu", "Arr_K7_Juu", 26)
+    bind("Arr_K7", "JpY", "Arr_K7_JpY", 10)
+    bind("Arr_K7", "JpT", "Arr_K7_JpT", 40)
+    bind("Arr_K7", "Jpp", "Arr_K7_Jpp", 40)
+    for s in states:
+        bind("Arr_J" + s, "K4", "Arr_K4_J" + s, 22)
+        bind("Arr_J" + s, "K7", "Arr_K7_J" + s, 24)
+        bind("Arr_K4_K7", "J" + s, "Arr_K4_K7_J" + s, 42)
+    bind("K4", "Juu", "K4_Juu", 16)
+    bind("K4", "JpT", "K4_JpT", 28)
+    bind("K4", "JpY", "K4_JpY", 32)
+    bind("K4", "Jpp", "K4_Jpp", 32)
+    bind("K7", "Juu", "K7_Juu", 18)
+    bind("K7", "JpY", "K7_JpY", 30)
+    bind("K7", "JpT", "K7_JpT", 34)
+    bind("K7", "Jpp", "K7_Jpp", 34)
+    for pre in ("Arr_K4_J", "K4_J", "Arr_K4_K7_J"):          # MKK4 phosphorylates Tyr
+        cat(pre + "uu", pre + "pY", 36)
+        cat(pre + "pT", pre + "pp", 36)
+    for pre in ("Arr_K7_J", "K7_J", "Arr_K4_K7_J"):          # MKK7 phosphorylates Thr
+        cat(pre + "uu", pre + "pT", 37)
+        cat(pre + "pY", pre + "pp", 37)
+    obs = {"pTyr_jnk3": {s: 1 for s in sp if s.endswith("JpY") or s.endswith("Jpp")},
+           "pThr_jnk3": {s: 1 for s in sp if s.endswith("JpT") or s.endswith("Jpp")},
+           "all_jnk3": {s: 1 for s in sp if "J" in s}}
+    return MassActionNetwork("jarm", sp, par, rx,
+                             {"Arr": "Arr_0", "K4": "K4_0", "K7": "K7_0", "Juu": "Juu_0", "JpT": "JpT_0",
+                              "JpY": "JpY_0"}, obs)
+
+
+SHIPPED["jarm"] = jarm

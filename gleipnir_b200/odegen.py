@@ -155,29 +155,156 @@ class MassActionNetwork(object):
     def cooperative(self):
         return self.ns >= self.COOP_MIN_SPECIES
 
+    def coop_min_blocks(self):
+        """Resident blocks per SM the cooperative kernels are compiled for: 4 while the register row is at
+        most 16 wide, 3 for a 32-wide row (168 registers: no spills of the matrix row)."""
+        env = os.environ.get("GLEIPNIR_COOP_MIN_BLOCKS")
+        if env:
+            return int(env)
+        return 4 if self.plan().nc <= 16 else 3
+
+    def plan(self):
+        """Elimination plan of the cooperative solver (odeplan.CoopPlan), cached."""
+        if getattr(self, "_plan", None) is None:
+            from .odeplan import CoopPlan
+            self._plan = CoopPlan(self)
+        return self._plan
+
+    def coop_tables(self):
+        """Index tables of the cooperative solver's right-hand side and Jacobian (csrc/ode_coop.cuh), species in
+        the plan's internal numbering.  Everything a lane needs is a list of positions in two small
+        shared-memory value tables the group refreshes once per state:
+
+          sv[2r], sv[2r+1]            = v_r, -v_r                      (reaction rates, both signs)
+          sd[4r .. 4r+3]              = dv_r/dy_a, -dv_r/dy_a, dv_r/dy_b, -dv_r/dy_b
+
+        so that  f_i = sum of sv[ftab[e][i]]  and  J_iq = sum of sd[...] over the entries of a segment of
+        jtab[.][i]  -- loads with addresses known up front and adds, no per-entry decoding of the network."""
+        pl = self.plan()
+        gl, nc, nx, ns = pl.gl, pl.nc, pl.nx, self.ns
+        inv = pl.inv
+        isp = lambda name: inv[self._sp(name)]
+        nr = len(self.reactions)
+        nrm = (nr + gl - 1) // gl
+        nrp = nrm * gl
+        ONE = ns                                             # y[NS] = 1.0: second "reactant" of a unimolecular step
+        ZV, ZD = 2 * nrp, 4 * nrp                            # slots holding 0.0 (list padding)
+        rtab = []
+        for r in range(nrp):
+            if r < nr:
+                reac = self.reactions[r][1]
+                a, b = isp(reac[0]), (isp(reac[1]) if len(reac) > 1 else ONE)
+            else:
+                a = b = ONE
+            rtab.append(a | (b << 16))
+        f_lists = [[] for _ in range(ns)]                    # per internal species: sv indices
+        j_lists = [dict() for _ in range(ns)]                # per internal species: {column: [sd indices]}
+        for r, (k, reac, prod, sf) in enumerate(self.reactions):
+            for name in set(reac) | set(prod):
+                net = prod.count(name) - reac.count(name)
+                if not net:
+                    continue
+                i = isp(name)
+                f_lists[i] += [2 * r + (0 if net > 0 else 1)] * abs(net)
+                sgn = 0 if net > 0 else 1
+                a = isp(reac[0])
+                j_lists[i].setdefault(a, []).extend([4 * r + sgn] * abs(net))
+                if len(reac) > 1:
+                    b = isp(reac[1])
+                    j_lists[i].setdefault(b, []).extend([4 * r + 2 + sgn] * abs(net))
+
+        def ftable(species, width):
+            depth = max([len(f_lists[s]) for s in species] + [1])
+            tab = [ZV] * (depth * width)
+            for lane, s in enumerate(species):
+                for e, idx in enumerate(f_lists[s]):
+                    tab[e * width + lane] = idx
+            return depth, tab
+
+        def jtable(species, width):
+            flat = []
+            for s in species:
+                ent = []
+                for col in sorted(j_lists[s]):
+                    terms = j_lists[s][col]
+                    for t, idx in enumerate(terms):          # bit 24: first term of this (row, column) sum
+                        ent.append(idx | (col << 16) | ((1 << 24) if t == 0 else 0))
+                flat.append(ent)
+            depth = max([len(e) for e in flat] + [1])
+            tab = [ZD] * (depth * width)                     # lanes without a row: add 0.0 into column 0 of a dump row
+            for lane, ent in enumerate(flat):
+                for e in range(depth):                       # padding: add 0.0 to the last sum and store it again
+                    tab[e * width + lane] = ent[e] if e < len(ent) else (ZD | (((ent[-1] >> 16) & 0xff) << 16) if ent else ZD)
+            return depth, tab
+
+        nxa = max(nx, 1)
+        ef, ftab = ftable(list(range(nc)), gl)
+        ef2, ftab2 = ftable(list(range(nc, ns)), nxa)
+        ej, jtab = jtable(list(range(nc)), gl)
+        ej2, jtab2 = jtable(list(range(nc, ns)), nxa)
+        ld = ns
+        while ld % 4 != 2:                                   # 16-byte aligned rows whose 128-bit loads spread over the banks
+            ld += 1
+        return dict(nrm=nrm, nrp=nrp, rtab=rtab, ef=ef, ftab=ftab, ef2=ef2, ftab2=ftab2, ej=ej, jtab=jtab, ej2=ej2,
+                    jtab2=jtab2, ld=ld, gl=gl, nc=nc, nx=nx, nxa=nxa, ns=ns)
+
+    def emulate_rhs_jac(self, y, p):
+        """f and J (ORIGINAL numbering) computed the way the device does, from coop_tables(); CPU tests compare
+        it with the oracle's right-hand side."""
+        T = self.coop_tables()
+        pl = self.plan()
+        ns, nc, gl, nxa = T["ns"], T["nc"], T["gl"], T["nxa"]
+        yi = np.ones(ns + 1)
+        yi[:ns] = np.asarray(y, dtype=np.float64)[pl.perm]
+        c = np.zeros(T["nrp"])
+        for r, (k, reac, prod, sf) in enumerate(self.reactions):
+            c[r] = sf * p[self._pp(k)]
+        sv = np.zeros(2 * T["nrp"] + 2)
+        sd = np.zeros(4 * T["nrp"] + 2)
+        for r in range(T["nrp"]):
+            a, b = T["rtab"][r] & 0xffff, T["rtab"][r] >> 16
+            cy = c[r] * yi[b]
+            v, da, db = cy * yi[a], cy, c[r] * yi[a]
+            sv[2 * r], sv[2 * r + 1] = v, -v
+            sd[4 * r:4 * r + 4] = [da, -da, db, -db]
+        f = np.zeros(ns)
+        J = np.zeros((ns, ns))
+        for slot, (width, ef, ftab, ej, jtab, base) in enumerate(((gl, T["ef"], T["ftab"], T["ej"], T["jtab"], 0),
+                                                               (nxa, T["ef2"], T["ftab2"], T["ej2"], T["jtab2"], nc))):
+            for lane in range(width):
+                if base + lane >= ns or (slot == 0 and lane >= nc):
+                    continue
+                f[base + lane] = sum(sv[ftab[e * width + lane]] for e in range(ef))
+                acc = 0.0
+                for e in range(ej):
+                    w = jtab[e * width + lane]
+                    acc = sd[w & 0xffff] + (0.0 if w >> 24 else acc)
+                    J[base + lane, (w >> 16) & 0xff] = acc
+        perm = np.array(pl.perm)
+        fo = np.zeros(ns)
+        fo[perm] = f
+        Jo = np.zeros((ns, ns))
+        Jo[np.ix_(perm, perm)] = J
+        return fo, Jo
+
     def cuda_tables(self):
-        """Table form of the network for the cooperative solver (csrc/ode_coop.cuh)."""
-        ns = self.ns
-        if ns > 32:
-            raise ValueError("networks with more than 32 species are not supported yet")
+        """Table form of the network for the cooperative solver (csrc/ode_coop.cuh), species in the
+        plan's internal numbering, plus the generated elimination / substitution code."""
         for k, reac, prod, sf in self.reactions:
             if not 1 <= len(reac) <= 2:
                 raise ValueError("the cooperative solver handles uni- and bimolecular mass-action reactions")
-        gl = 16 if ns <= 16 else 32
-        rx_a = [self._sp(r[1][0]) for r in self.reactions]
-        rx_b = [self._sp(r[1][1]) if len(r[1]) > 1 else -1 for r in self.reactions]
+        pl = self.plan()
+        T = self.coop_tables()
+        ns = self.ns
+        if ns + 1 >= 256 or 4 * T["nrp"] + 1 >= 65536:
+            raise ValueError("network too large for the cooperative solver's 8/16-bit index tables")
+        inv = pl.inv                                        # original species index -> internal
+        order = [self.species[s] for s in pl.perm]          # internal -> species name
+        isp = lambda name: inv[self._sp(name)]
         rx_k = [self._pp(r[0]) for r in self.reactions]
         rx_sf = [r[3] for r in self.reactions]
-        row_ptr, row_rx, row_coef = [0], [], []
-        for s_ in self.species:
-            for i, (k, reac, prod, sf) in enumerate(self.reactions):
-                net = prod.count(s_) - reac.count(s_)
-                if net:
-                    row_rx.append(i)
-                    row_coef.append(net)
-            row_ptr.append(len(row_rx))
         init_kind, init_val, init_par = [], [], []
-        for s_ in self.species:
+        for s_ in order:
             v = self.initials.get(s_, 0.0)
             init_kind.append(1 if isinstance(v, str) else 0)
             init_par.append(self._pp(v) if isinstance(v, str) else 0)
@@ -185,7 +312,7 @@ class MassActionNetwork(object):
         obs_ptr, obs_sp, obs_coef = [0], [], []
         for name in self.obs_names:
             for s_, c in self.observables[name].items():
-                obs_sp.append(self._sp(s_))
+                obs_sp.append(isp(s_))
                 obs_coef.append(float(c))
             obs_ptr.append(len(obs_sp))
 
@@ -193,28 +320,42 @@ class MassActionNetwork(object):
             body = ", ".join(repr(v) if ctype == "double" else str(v) for v in vals) or "0"
             return "__device__ const %s T_%s[] = {%s};" % (ctype, name, body)
 
-        tables = [arr("int", "rx_a", rx_a), arr("int", "rx_b", rx_b), arr("int", "rx_k", rx_k),
-                  arr("double", "rx_sf", rx_sf), arr("int", "row_ptr", row_ptr), arr("int", "row_rx", row_rx),
-                  arr("int", "row_coef", row_coef), arr("int", "init_kind", init_kind),
-                  arr("double", "init_val", init_val), arr("int", "init_par", init_par),
-                  arr("int", "obs_ptr", obs_ptr), arr("int", "obs_sp", obs_sp), arr("double", "obs_coef", obs_coef)]
-        acc = []
-        for t, name in (("int", "rx_a"), ("int", "rx_b"), ("int", "rx_k"), ("double", "rx_sf"), ("int", "row_ptr"),
-                        ("int", "row_rx"), ("int", "row_coef"), ("int", "init_kind"), ("double", "init_val"),
-                        ("int", "init_par"), ("int", "obs_ptr"), ("int", "obs_sp"), ("double", "obs_coef")):
-            acc.append("    static __device__ __forceinline__ %s %s(int i) { return T_%s[i]; }" % (t, name, name))
-        struct = ["struct Net {",
-                  "    static constexpr int NS = %d, NP = %d, NR = %d, NOBS = %d, GL = %d;"
-                  % (ns, self.np_, len(self.reactions), len(self.obs_names), gl)] + acc + ["};"]
+        spec = (("int", "rx_k", rx_k), ("double", "rx_sf", rx_sf), ("int", "init_kind", init_kind),
+                ("double", "init_val", init_val), ("int", "init_par", init_par), ("int", "obs_ptr", obs_ptr),
+                ("int", "obs_sp", obs_sp), ("double", "obs_coef", obs_coef),
+                ("unsigned int", "rtab", T["rtab"]), ("unsigned short", "ftab", T["ftab"]),
+                ("unsigned short", "ftab2", T["ftab2"]), ("unsigned int", "jtab", T["jtab"]),
+                ("unsigned int", "jtab2", T["jtab2"]))
+        tables = [arr(t, n, v) for t, n, v in spec]
+        acc = ["    static __device__ __forceinline__ %s %s(int i) { return T_%s[i]; }" % (t, n, n) for t, n, v in spec]
+        struct = ["// species, internal order: " + " ".join(order),
+                  "struct Net {",
+                  "    static constexpr int NS = %d, NC = %d, NX = %d, NXA = %d, NP = %d, NR = %d, NOBS = %d, GL = %d, "
+                  "LD = %d;" % (ns, pl.nc, pl.nx, T["nxa"], self.np_, len(self.reactions), len(self.obs_names), pl.gl,
+                                T["ld"]),
+                  "    static constexpr int NRM = %d, NRP = %d, EF = %d, EF2 = %d, EJ = %d, EJ2 = %d;"
+                  % (T["nrm"], T["nrp"], T["ef"], T["ef2"], T["ej"], T["ej2"])]
+        struct += acc
+        struct += ["    // M = diag*I - J factored in place: lane i holds core row i (L below the diagonal, U on and",
+                   "    // above it), A the lane's multipliers of the leaf columns; J = Jacobian rows in shared memory",
+                   "    static __device__ __forceinline__ bool lu(double (&M)[NC], double (&A)[NXA], const double *J, "
+                   "double diag, int lane,",
+                   "                                              unsigned gmask, int gbase, double &inv_d, double &inv_d2) {",
+                   pl.cuda_lu(), "    }",
+                   "    static __device__ __forceinline__ void solve(const double (&M)[NC], const double (&A)[NXA], "
+                   "const double *J, double inv_d,",
+                   "                                                 double inv_d2, double &b, double &b2, int lane, "
+                   "unsigned gmask, int gbase) {",
+                   pl.cuda_solve(), "    }", "};"]
         return "\n".join(tables + struct)
 
-    def plugin_source(self):
-        if self.cooperative:
-            return COOP_PLUGIN_TEMPLATE % dict(name=self.name, struct=self.cuda_tables())
+    def plugin_source(self, coop=None):
+        if self.cooperative if coop is None else coop:
+            return COOP_PLUGIN_TEMPLATE % dict(name=self.name, struct=self.cuda_tables(), min_blocks=self.coop_min_blocks())
         return PLUGIN_TEMPLATE % dict(name=self.name, struct=self.cuda_struct())
 
-    def source_hash(self):
-        h = hashlib.sha256(self.plugin_source().encode())
+    def source_hash(self, coop=None):
+        h = hashlib.sha256(self.plugin_source(coop).encode())
         for fn in ("ode_like.cuh", "ode_coop.cuh", "walker.cuh", "loglike.cuh", "likelihoods.cuh", "engine.cuh", "common.cuh",
                    "priors.cuh", "philox.cuh", "select.cuh"):
             with open(os.path.join(CSRC, fn), "rb") as f:
@@ -249,6 +390,7 @@ GL_API void gl_plugin_info(int *ns, int *np, int *nobs) {
 
 
 COOP_PLUGIN_TEMPLATE = r'''// GENERATED by gleipnir_b200/odegen.py for network "%(name)s" (cooperative solver) -- do not edit.
+#define GL_COOP_MIN_BLOCKS %(min_blocks)d
 #include "ode_coop.cuh"
 
 namespace {
@@ -257,7 +399,8 @@ namespace {
 
 extern "C" {
 GL_API int gl_plugin_walk_launch(const void *P, const void *M, void *stream) {
-    return gl::walk_coop_launch<Net>(*(const gl::WalkParams *)P, *(const gl::ModelDev *)M, (cudaStream_t)stream);
+    const gl::ModelDev &md = *(const gl::ModelDev *)M;          // s0 = blob word 8: number of conditions
+    return gl::walk_coop_launch<Net>(*(const gl::WalkParams *)P, md, md.s0 >= 1.0 ? (int)md.s0 : 1, (cudaStream_t)stream);
 }
 GL_API int gl_plugin_eval_launch(const void *M, const double *x, long long n, double *out, void *stream) {
     return gl::ode_coop_eval_launch<Net>(*(const gl::ModelDev *)M, x, n, out, (cudaStream_t)stream);
@@ -266,21 +409,23 @@ GL_API const char *gl_plugin_last_error(void) { return gl::error_buffer(); }
 GL_API void gl_plugin_info(int *ns, int *np, int *nobs) {
     *ns = Net::NS; *np = Net::NP; *nobs = Net::NOBS;
 }
+GL_API int gl_plugin_counters(unsigned long long *out3, int reset) { return gl::coop_counters<Net>(out3, reset); }
 }
 '''
 
 
-def compile_plugin(network, force=False):
-    """nvcc the generated source into gleipnir_b200/_plugins/ode_<name>_<hash>.so (cached)."""
+def compile_plugin(network, force=False, coop=None):
+    """nvcc the generated source into gleipnir_b200/_plugins/ode_<name>_<hash>.so (cached).
+    coop=True forces the cooperative (lane-group) solver, which the protocol likelihood needs."""
     from .build import NVCC_FLAGS, _nvcc
     os.makedirs(PLUGIN_DIR, exist_ok=True)
-    tag = "%s_%s" % (network.name, network.source_hash())
+    tag = "%s_%s" % (network.name, network.source_hash(coop))
     so = os.path.join(PLUGIN_DIR, "ode_%s.so" % tag)
     if os.path.exists(so) and not force:
         return so
     cu = os.path.join(PLUGIN_DIR, "ode_%s.cu" % tag)
     with open(cu, "w") as f:
-        f.write(network.plugin_source())
+        f.write(network.plugin_source(coop))
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", CSRC, "-shared", cu, "-o", so, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -291,13 +436,82 @@ def compile_plugin(network, force=False):
 _loaded = {}
 
 
-def load_plugin(network):
-    so = compile_plugin(network)
+def load_plugin(network, coop=None):
+    so = compile_plugin(network, coop=coop)
     if so not in _loaded:
         lib = ctypes.CDLL(so)
         lib.gl_plugin_last_error.restype = ctypes.c_char_p
         _loaded[so] = lib
     return _loaded[so]
+
+
+def pack_protocol_blob(network, sampled, tspan, conditions, rows, like_type, rtol, atol, max_steps, preeq=None,
+                       cycles=None):
+    """Data block read by the cooperative solver (layout: csrc/ode_coop.cuh::ProtoBlob).
+
+    sampled     list of (parameter name, is_log10)
+    conditions  list (one per condition) of [(parameter index, value), ...] overrides
+    rows        list of dicts(cond, obs (index), scale, kind ('norm'|'halfnorm'), data[nt], sd[nt], mask[nt])
+    preeq       None | dict(t_end, zero_idx=[parameter indices], eq_tol=None|float)
+    cycles      None | dict(loc, scale, factors=[[(a, b, inverted), ...], ...])"""
+    nt, d = len(tspan), len(sampled)
+    ncond = len(conditions)
+    rows = sorted(rows, key=lambda r: r["cond"])             # stable: rows of a condition stay in the given order
+    nrows = len(rows)
+    header = np.zeros(48)
+    nominal = network.param_values.astype(np.float64)
+    pmap = np.array([network._pp(n) for n, _ in sampled], dtype=np.float64)
+    islog = np.array([1.0 if lg else 0.0 for _, lg in sampled])
+    meta = np.zeros(4 * nrows)
+    data, sd, mask, cterm = (np.zeros(nrows * nt) for _ in range(4))
+    sd[:] = 1.0
+    rowptr = np.zeros(ncond + 1)
+    stops, stopptr = [], [0]
+    for i, r in enumerate(rows):
+        kind = {"norm": 0, "halfnorm": 1}[r.get("kind", "norm")]
+        meta[4 * i:4 * i + 4] = [r["cond"], r["obs"], r.get("scale", 1.0), kind]
+        data[i * nt:(i + 1) * nt] = r["data"]
+        sd[i * nt:(i + 1) * nt] = r["sd"]
+        mask[i * nt:(i + 1) * nt] = r["mask"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lsd = np.log(np.asarray(r["sd"], dtype=np.float64))
+        # scipy: norm.logpdf = -z^2/2 - log(sd) - log(2 pi)/2; halfnorm.logpdf = -z^2/2 + log(2/pi)/2 - log(sd), z >= 0
+        cterm[i * nt:(i + 1) * nt] = (0.5 * np.log(2.0 / np.pi) - lsd) if kind == 1 else (-lsd - 0.5 * np.log(2.0 * np.pi))
+        rowptr[r["cond"] + 1:] += 1
+    for c in range(ncond):
+        m = np.zeros(nt, dtype=bool)
+        for r in rows:
+            if r["cond"] == c:
+                m |= np.asarray(r["mask"]) != 0
+        stops += [float(i) for i in np.nonzero(m)[0]]
+        stopptr.append(len(stops))
+    overptr, overidx, overval = [0], [], []
+    for ov in conditions:
+        for i, v in ov:
+            overidx.append(float(i))
+            overval.append(float(v))
+        overptr.append(len(overidx))
+    zeroidx = [float(i) for i in (preeq["zero_idx"] if preeq else [])]
+    cycptr, cycfac = [0], []
+    if cycles:
+        for factors in cycles["factors"]:
+            for a, b, inv in factors:
+                cycfac += [float(a), float(b), 1.0 if inv else 0.0]
+            cycptr.append(len(cycfac) // 3)
+    parts = [nominal, pmap, islog, np.asarray(tspan, dtype=np.float64), meta, data, sd, mask, cterm, rowptr,
+             np.array(overptr, dtype=np.float64), np.array(overidx), np.array(overval), np.array(zeroidx),
+             np.array(cycptr, dtype=np.float64), np.array(cycfac), np.array(stopptr, dtype=np.float64), np.array(stops)]
+    off = 48
+    offs = []
+    for a in parts:
+        offs.append(off)
+        off += len(a)
+    eq_tol = preeq.get("eq_tol") if preeq else None
+    header[0:16] = [d, len(nominal), nt, like_type, max_steps, rtol, atol, nrows, ncond, 1.0 if preeq else 0.0,
+                    preeq["t_end"] if preeq else 0.0, -1.0 if eq_tol is None else eq_tol, len(zeroidx),
+                    len(cycptr) - 1, cycles["loc"] if cycles else 0.0, cycles["scale"] if cycles else 1.0]
+    header[16:16 + len(offs)] = offs
+    return np.ascontiguousarray(np.concatenate([header] + [np.asarray(a, dtype=np.float64) for a in parts]))
 
 
 def pack_blob(network, sampled, tspan, rows, like_type, rtol, atol, max_steps):
@@ -358,15 +572,87 @@ class OdeNetworkLogLikelihood(DeviceLogLikelihood):
                 full_s[idx] = np.asarray(sd, dtype=np.float64)
             full_m[idx] = 1.0
             self.rows.append((network.obs_names.index(obs), full_d, full_s, full_m))
-        self._blob = pack_blob(network, self.sampled, self.tspan, self.rows, LIKE_TYPES[kind], self.rtol, self.atol,
-                               self.max_steps)
+        self._coop = network.cooperative
+        if self._coop:                 # one condition, no pre-equilibration, no cycle terms
+            prows = [dict(cond=0, obs=o, scale=1.0, kind="norm", data=fd, sd=fs, mask=fm) for o, fd, fs, fm in self.rows]
+            self._blob = pack_protocol_blob(network, self.sampled, self.tspan, [[]], prows, LIKE_TYPES[kind], self.rtol,
+                                            self.atol, self.max_steps)
+        else:
+            self._blob = pack_blob(network, self.sampled, self.tspan, self.rows, LIKE_TYPES[kind], self.rtol, self.atol,
+                                   self.max_steps)
         self._plugin = None
 
     def _create(self, lib):
-        self._plugin = load_plugin(self.network)
+        self._plugin = load_plugin(self.network, coop=self._coop)
         walk = ctypes.cast(self._plugin.gl_plugin_walk_launch, ctypes.c_void_p)
         ev = ctypes.cast(self._plugin.gl_plugin_eval_launch, ctypes.c_void_p)
         h = ctypes.c_void_p()
         _lib.check(lib.gl_model_create_external(self.ndim, walk, ev, self._blob.ctypes.data_as(ctypes.c_void_p),
                                                 self._blob.nbytes, ctypes.byref(h)))
         return h
+
+    def counters(self, reset=False):
+        """Work counters of the cooperative solver since the last reset: likelihood evaluations actually
+        integrated, ODE solves, Rosenbrock steps attempted (all likelihood objects of one network share them)."""
+        if not self._coop:
+            raise TypeError("work counters exist for the cooperative solver only")
+        self.device_model()
+        out = (ctypes.c_ulonglong * 3)()
+        _lib.check(self._plugin.gl_plugin_counters(out, 1 if reset else 0))
+        return dict(evals=int(out[0]), solves=int(out[1]), steps=int(out[2]))
+
+
+class OdeProtocolLogLikelihood(OdeNetworkLogLikelihood):
+    """Multi-condition ODE likelihood: the structure of ``examples/pysb_jarm/run_jarm_multinest.py:92-143``.
+
+    network      MassActionNetwork
+    sampled      names of the sampled parameters (``params[mask] = 10**Y``, :94)
+    tspan        output time points (:26)
+    conditions   one dict {parameter name or index: value} of overrides per simulated condition (:110-111, 122-123)
+    rows         data terms (:31-43, 126-134): dicts with ``cond``, ``obs`` (observable name), ``scale`` (the
+                 simulated observable is divided by it, :57), ``kind`` 'norm' | 'halfnorm', ``data``/``sd`` at the
+                 tspan indices ``mask``
+    preeq        None, or dict(t_end=100.0, zero=[parameter names or indices], eq_tol=None): every condition is first
+                 integrated to t_end with the listed constants zeroed and the main solve starts from that state
+                 (:105-119); with eq_tol the state must satisfy max|dy/dt| <= eq_tol or the likelihood is -inf
+                 (the role of the reference's external ``pre_equilibration``, which raises when no equilibrium is found)
+    cycles       None, or dict(loc, scale, factors): thermodynamic-cycle products scored by norm(loc, scale) (:72-103)
+    """
+
+    def __init__(self, network, sampled, tspan, conditions, rows, preeq=None, cycles=None, log10=True, rtol=1e-8,
+                 atol=1e-12, max_steps=100000):
+        DeviceLogLikelihood.__init__(self)
+        self.network = network
+        self.sampled = [(n, bool(log10)) for n in sampled]
+        self.ndim = len(self.sampled)
+        self.tspan = np.asarray(tspan, dtype=np.float64)
+        self.kind = "snlpdf"
+        self.rtol, self.atol, self.max_steps = float(rtol), float(atol), int(max_steps)
+        nt = len(self.tspan)
+        pidx = lambda k: network._pp(k) if isinstance(k, str) else int(k)
+        self.conditions = [[(pidx(k), float(v)) for k, v in c.items()] for c in conditions]
+        self.rows = []
+        for r in rows:
+            idx = np.arange(nt) if r.get("mask") is None else np.asarray(r["mask"], dtype=int)
+            fd, fs, fm = np.zeros(nt), np.ones(nt), np.zeros(nt)
+            fd[idx], fs[idx], fm[idx] = np.asarray(r["data"], dtype=np.float64), np.asarray(r["sd"], dtype=np.float64), 1.0
+            obs = r["obs"]
+            self.rows.append(dict(cond=int(r["cond"]), obs=network.obs_names.index(obs) if isinstance(obs, str) else int(obs),
+                                  scale=float(r.get("scale", 1.0)), kind=r.get("kind", "norm"), data=fd, sd=fs, mask=fm))
+        self.preeq = None
+        if preeq:
+            self.preeq = dict(t_end=float(preeq.get("t_end", 100.0)), zero_idx=[pidx(k) for k in preeq.get("zero", [])],
+                              eq_tol=preeq.get("eq_tol"), n_points=int(preeq.get("n_points", 100)))
+        self.cycles = None
+        if cycles:
+            self.cycles = dict(loc=float(cycles.get("loc", 1.0)), scale=float(cycles.get("scale", 1.0)),
+                               factors=[[(pidx(a), pidx(b), bool(inv)) for a, b, inv in f] for f in cycles["factors"]])
+        self._coop = True
+        self._blob = pack_protocol_blob(network, self.sampled, self.tspan, self.conditions, self.rows, LIKE_TYPES["snlpdf"],
+                                        self.rtol, self.atol, self.max_steps, self.preeq, self.cycles)
+        self._plugin = None
+
+    def oracle_protocol(self):
+        """The same protocol as the plain-data dict ``oracle.ode.protocol_loglike`` consumes (tests, bench baseline)."""
+        return dict(sampled_idx=[self.network._pp(n) for n, _ in self.sampled], log10=self.sampled[0][1],
+                    tspan=self.tspan, conditions=self.conditions, preeq=self.preeq, cycles=self.cycles, rows=self.rows)

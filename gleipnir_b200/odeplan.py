@@ -1,0 +1,322 @@
+"""Symbolic analysis of a mass-action network for the cooperative (warp-per-system) ODE solver.
+
+The solver (csrc/ode_coop.cuh) factors ``M = I/(gamma h) - J`` once per Rosenbrock step and
+back-substitutes four times.  One warp (or half-warp) owns one system: lane i holds ROW i of M in
+registers.  Everything that depends only on the network's STRUCTURE is decided here, once, and
+emitted as straight-line CUDA (no loops over zeros, no runtime indices into the register row):
+
+* **species order** -- a minimum-degree elimination order on the Jacobian's sparsity pattern,
+  so that the rows of U stay short: a lane-uniform elimination step costs one warp-wide FMA per
+  structural nonzero of the pivot row, whether or not a given lane's multiplier is zero;
+* **leaf species** -- a network with more species than lanes (NS > 32) keeps a 32-row *core* in
+  the lanes and eliminates NS-32 mutually independent low-degree species first (block
+  elimination): their rows stay in shared memory, are never updated (they are eliminated first
+  and do not couple to each other), and cost a handful of FMAs each.  Lane l carries leaf l's
+  vector entries in a second register slot;
+* **symbolic LU** of the core with fill, giving the (pivot, column) update list;
+* **level schedules** of the two triangular solves: columns whose unknowns do not depend on each
+  other broadcast together, so the shuffle->FMA dependency chain is as long as the elimination
+  DAG is deep, not as long as the matrix is wide.
+
+``emulate_solve`` executes the very same plan with numpy lane vectors; the CPU tests compare it
+with ``numpy.linalg.solve`` so a wrong pattern or schedule is caught without a GPU.
+
+Reference for what is being integrated: the ScipyOdeSimulator runs behind
+``gleipnir/pysb_utilities/nestedsample_it.py:287`` and ``examples/pysb_jarm/run_jarm_multinest.py:116,125``.
+"""
+import numpy as np
+
+MAX_LANES = 32
+
+
+def jacobian_pattern(network):
+    """Boolean [ns, ns]: entry (s, q) is True when d f_s / d y_q is structurally nonzero."""
+    ns = network.ns
+    P = np.zeros((ns, ns), dtype=bool)
+    for k, reac, prod, sf in network.reactions:
+        rows = set()
+        for s in set(reac) | set(prod):
+            if prod.count(s) - reac.count(s) != 0:
+                rows.add(network._sp(s))
+        for q in set(reac):
+            for s in rows:
+                P[s, network._sp(q)] = True
+    return P
+
+
+class CoopPlan(object):
+    """Elimination plan in INTERNAL species numbering: internal index i < nc is core row i (lane i),
+    internal index nc + l is leaf l (second slot of lane l).  ``perm[i]`` = original species index."""
+
+    def __init__(self, network, max_lanes=MAX_LANES):
+        ns = network.ns
+        P0 = jacobian_pattern(network) | np.eye(ns, dtype=bool)
+        sym = P0 | P0.T
+        nx = max(0, ns - max_lanes)
+        leaves = self._pick_leaves(sym, nx)
+        if len(leaves) < nx:
+            raise ValueError("network %s has %d species: the cooperative solver needs %d mutually independent "
+                             "leaf species next to its %d-row core and found %d"
+                             % (network.name, ns, nx, max_lanes, len(leaves)))
+        core = [s for s in range(ns) if s not in leaves]
+        # pattern after leaf elimination (fill among each leaf's neighbours), in original numbering
+        P = P0.copy()
+        for e in leaves:
+            rows = [i for i in core if P[i, e]]
+            cols = [q for q in core if P[e, q]]
+            for i in rows:
+                P[i, cols] = True
+        order = self._min_degree(P, core)
+        self.perm = order + leaves
+        self.ns, self.nc, self.nx = ns, len(order), len(leaves)
+        self.gl = 16 if self.nc <= 16 else 32
+        inv = {s: i for i, s in enumerate(self.perm)}
+        self.inv = inv
+        n = ns
+        Q = np.zeros((n, n), dtype=bool)                       # original pattern, internal numbering
+        for s in range(ns):
+            for q in range(ns):
+                if P0[s, q]:
+                    Q[inv[s], inv[q]] = True
+        self.pattern0 = Q.copy()
+        nc = self.nc
+        # ---- leaf elimination --------------------------------------------------------------------
+        self.leaf_rows = []                                    # per leaf: core columns of its row
+        self.leaf_cols = []                                    # per leaf: core rows of its column
+        for l in range(self.nx):
+            e = nc + l
+            assert not Q[e, nc:][np.arange(self.nx) != l].any() and not Q[nc:, e][np.arange(self.nx) != l].any()
+            cols = [q for q in range(nc) if Q[e, q]]
+            rows = [i for i in range(nc) if Q[i, e]]
+            self.leaf_rows.append(cols)
+            self.leaf_cols.append(rows)
+            for i in rows:
+                Q[i, cols] = True
+        # ---- symbolic LU of the core ----------------------------------------------------------------
+        self.lu_ops = []                                       # (c, [q > c with U_cq != 0])
+        for c in range(nc):
+            cols = [q for q in range(c + 1, nc) if Q[c, q]]
+            rows = [i for i in range(c + 1, nc) if Q[i, c]]
+            self.lu_ops.append((c, cols))
+            for i in rows:
+                Q[i, cols] = True
+        self.filled = Q
+        Lp = np.tril(Q[:nc, :nc], -1)
+        Up = np.triu(Q[:nc, :nc], 1)
+        # ---- level schedules -------------------------------------------------------------------------
+        lev_f = [0] * nc
+        for c in range(nc):
+            deps = [lev_f[q] for q in range(c) if Lp[c, q]]
+            lev_f[c] = 1 + max(deps) if deps else 0
+        lev_b = [0] * nc
+        for c in range(nc - 1, -1, -1):
+            deps = [lev_b[q] for q in range(c + 1, nc) if Up[c, q]]
+            lev_b[c] = 1 + max(deps) if deps else 0
+        # forward: a column only broadcasts if some row below uses it
+        self.fwd_levels = [[c for c in range(nc) if lev_f[c] == lv and Lp[:, c].any()]
+                           for lv in range(max(lev_f) + 1 if nc else 0)]
+        self.fwd_levels = [lv for lv in self.fwd_levels if lv]
+        # backward: every column is scaled at its level; it broadcasts only if some row above uses it
+        self.bwd_levels = [([c for c in range(nc) if lev_b[c] == lv],
+                            [c for c in range(nc) if lev_b[c] == lv and Up[:, c].any()])
+                           for lv in range(max(lev_b) + 1 if nc else 0)]
+        self.nnz_u = int(Up.sum())
+        self.nnz_l = int(Lp.sum())
+
+    @staticmethod
+    def _pick_leaves(sym, nx):
+        """nx mutually non-adjacent species of lowest degree (greedy)."""
+        if nx == 0:
+            return []
+        deg = sym.sum(axis=1)
+        chosen = []
+        for s in np.argsort(deg, kind="stable"):
+            if all(not sym[s, e] for e in chosen):
+                chosen.append(int(s))
+                if len(chosen) == nx:
+                    break
+        return chosen
+
+    @staticmethod
+    def _min_degree(P, core):
+        """Greedy Markowitz order on the (unsymmetric) pattern restricted to `core`."""
+        P = P.copy()
+        left = list(core)
+        order = []
+        while left:
+            best, cost = None, None
+            for s in left:
+                r = sum(1 for q in left if q != s and P[s, q])
+                c = sum(1 for i in left if i != s and P[i, s])
+                key = (r * c, r, s)
+                if cost is None or key < cost:
+                    best, cost = s, key
+            order.append(best)
+            left.remove(best)
+            rows = [i for i in left if P[i, best]]
+            cols = [q for q in left if P[best, q]]
+            for i in rows:
+                P[i, cols] = True
+        return order
+
+    # ---- the plan executed with numpy lane vectors (what the generated CUDA does) -----------------
+    def emulate_solve(self, J, diag, rhs):
+        """Solve (diag*I - J) x = rhs with the plan; J, rhs in ORIGINAL numbering.  Returns x (original
+        numbering) or None when a pivot vanishes."""
+        ns, nc, nx, gl = self.ns, self.nc, self.nx, self.gl
+        perm = np.array(self.perm)
+        Ji = np.asarray(J, dtype=np.float64)[np.ix_(perm, perm)]
+        bi = np.asarray(rhs, dtype=np.float64)[perm]
+        lane = np.arange(gl)
+        M = np.zeros((gl, nc))                                  # M[lane, q]
+        A = np.zeros((gl, max(nx, 1)))
+        for i in range(gl):
+            if i < nc:
+                M[i] = -Ji[i, :nc]
+                M[i, i] += diag
+                for l in range(nx):
+                    A[i, l] = -Ji[i, nc + l]
+            elif i < nc:
+                pass
+        inv_d2 = np.zeros(gl)
+        # leaf elimination
+        for l in range(nx):
+            e = nc + l
+            de = diag - Ji[e, e]
+            if not np.isfinite(de) or abs(de) <= 1e-300:
+                return None
+            ie = 1.0 / de
+            A[:, l] *= ie
+            for q in self.leaf_rows[l]:
+                M[:, q] += A[:, l] * Ji[e, q]                   # M_iq -= l_ie * M_eq, M_eq = -J_eq
+            inv_d2[l] = ie
+        # core LU
+        for c, cols in self.lu_ops:
+            piv = M[c, c]
+            if not np.isfinite(piv) or abs(piv) <= 1e-300:
+                return None
+            lm = M[:, c] * (1.0 / piv)
+            below = lane > c
+            M[below, c] = lm[below]
+            for q in cols:
+                pq = M[c, q]
+                M[below, q] = M[below, q] - lm[below] * pq
+        inv_d = np.array([1.0 / M[i, i] if i < nc else 1.0 for i in range(gl)])
+        # solve
+        b = np.zeros(gl)
+        b[:nc] = bi[:nc]
+        b2 = np.zeros(gl)
+        b2[:nx] = bi[nc:]
+        for l in range(nx):
+            b = b - A[:, l] * b2[l]
+        for level in self.fwd_levels:
+            t = {c: b[c] for c in level}
+            for c in level:
+                m = lane > c
+                b[m] = b[m] - M[m, c] * t[c]
+        for scale, bcast in self.bwd_levels:
+            for c in scale:
+                b[c] *= inv_d[c]
+            t = {c: b[c] for c in bcast}
+            for c in bcast:
+                m = lane < c
+                b[m] = b[m] - M[m, c] * t[c]
+        for l in range(nx):
+            e = nc + l
+            for q in self.leaf_rows[l]:
+                b2[l] += Ji[e, q] * b[q]
+            b2[l] *= inv_d2[l]
+        x = np.zeros(ns)
+        x[perm[:nc]] = b[:nc]
+        x[perm[nc:]] = b2[:nx]
+        return x
+
+    # ---- CUDA emission ---------------------------------------------------------------------------------
+    def cuda_lu(self):
+        """Body of Net::lu: factor in place.  Registers: M[NC] (this lane's core row), A[NXA] (its
+        entries in the leaf columns); J = the group's Jacobian rows in shared memory (leaf rows are
+        read from there); inv_d receives 1/U_ii of the lane's own row; returns the lane's verdict on
+        the pivots.  Branch-free: a lane at or above the pivot row takes part with a zero multiplier."""
+        nc, nx = self.nc, self.nx
+        out = ["        bool ok = true;"]
+        for l in range(nx):
+            e = nc + l
+            out.append("        {   // leaf %d (internal species %d)" % (l, e))
+            out.append("            const double de = diag - J[%d * LD + %d];" % (e, e))
+            out.append("            ok = ok & (fabs(de) > 1e-300);")
+            out.append("            const double ie = 1.0 / de;")
+            out.append("            A[%d] *= ie;" % l)
+            for q in self.leaf_rows[l]:
+                out.append("            M[%d] = fma(A[%d], J[%d * LD + %d], M[%d]);" % (q, l, e, q, q))
+            out.append("            inv_d2 = lane == %d ? ie : inv_d2;" % l)
+            out.append("        }")
+        for c, cols in self.lu_ops:
+            out.append("        {   // pivot %d" % c)
+            out.append("            const double piv = __shfl_sync(gmask, M[%d], gbase + %d);" % (c, c))
+            out.append("            ok = ok & (fabs(piv) > 1e-300);")
+            out.append("            const double ip = 1.0 / piv;")
+            out.append("            inv_d = lane == %d ? ip : inv_d;" % c)
+            if cols or any(c in lv for lv in self.fwd_levels):
+                out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
+                out.append("            M[%d] = lane > %d ? lz : M[%d];" % (c, c, c))
+                for q in cols:
+                    out.append("            M[%d] = fma(-lz, __shfl_sync(gmask, M[%d], gbase + %d), M[%d]);" % (q, q, c, q))
+            out.append("        }")
+        out.append("        return ok;")
+        return "\n".join(out)
+
+    def cuda_solve(self):
+        """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX)."""
+        nc, nx = self.nc, self.nx
+        out = []
+        for l in range(nx):
+            out.append("        { const double t = __shfl_sync(gmask, b2, gbase + %d); b = fma(-A[%d], t, b); }" % (l, l))
+        for level in self.fwd_levels:
+            out.append("        {")
+            for c in level:
+                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (c, c))
+            for c in level:
+                out.append("            if (lane > %d) b = fma(-M[%d], t%d, b);" % (c, c, c))
+            out.append("        }")
+        for scale, bcast in self.bwd_levels:
+            mask = 0
+            for c in scale:
+                mask |= 1 << c
+            out.append("        {")
+            out.append("            if ((0x%xu >> lane) & 1u) b *= inv_d;" % mask)
+            for c in bcast:
+                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (c, c))
+            for c in bcast:
+                out.append("            if (lane < %d) b = fma(-M[%d], t%d, b);" % (c, c, c))
+            out.append("        }")
+        if nx:
+            used = sorted({q for l in range(nx) for q in self.leaf_rows[l]})
+            out.append("        {")
+            for q in used:
+                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (q, q))
+            for l in range(nx):
+                e = nc + l
+                out.append("            if (lane == %d) {" % l)
+                for q in self.leaf_rows[l]:
+                    out.append("                b2 = fma(J[%d * LD + %d], t%d, b2);" % (e, q, q))
+                out.append("                b2 *= inv_d2;")
+                out.append("            }")
+            out.append("        }")
+        return "\n".join(out)
+
+    def flops_dense(self, n_reactions):
+        """SURVEY 8d's algorithmic count per Rosenbrock step: Jacobian 2r*order, LU 2/3 n^3,
+        4 x (RHS 3r + solve 2 n^2)."""
+        n = self.ns
+        return 4.0 * n_reactions + 2.0 / 3.0 * n ** 3 + 4.0 * (3.0 * n_reactions + 2.0 * n * n)
+
+    def flops_executed(self, n_reactions):
+        """FMAs x 2 the generated code actually issues per step, counted per USEFUL lane entry
+        (structural nonzeros), not per warp instruction."""
+        lu = 2.0 * sum(len(self.leaf_rows[l]) * len(self.leaf_cols[l]) for l in range(self.nx))
+        Q = self.filled
+        for c, cols in self.lu_ops:
+            rows = int(Q[c + 1:self.nc, c].sum())
+            lu += 2.0 * rows * len(cols) + rows
+        solve = 2.0 * (self.nnz_l + self.nnz_u + self.nc + sum(len(r) + len(c) for r, c in zip(self.leaf_rows, self.leaf_cols)))
+        return 4.0 * n_reactions + lu + 4.0 * (3.0 * n_reactions + solve)
