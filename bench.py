@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- logL evals/s and time-to-converged logZ of the B200 Nested Sampling path.
+"""bench.py -- logL evals/s of the B200 Nested Sampling path on BASELINE.json's headline config.
 
-Workload (BASELINE.json configs[1], concretised in SURVEY 8d "C2"): 2-D egg-carton
-log-likelihood (2 + cos x cos y)^5, priors uniform(0, 10*pi), population 10^4 per GPU,
-MetropolisComponentWiseHardNSRejection(iterations=50, tuning_cycles=2), stop at
-RemainingPriorMass(1e-6) -> 138 163 deaths, truth ln Z ~= 235.88.
+Headline workload (BASELINE.json configs[4], SURVEY 8d "C5"): the JARM likelihood
+(examples/pysb_jarm/run_jarm_multinest.py:72-143) on the synthetic JARM-shaped network
+(34 species, 84 reactions, 50 parameters, 18 sampled; gleipnir_b200/jarm.py), N = 10^5 live points,
+sampler MetropolisComponentWiseHardNSRejection(iterations=10, burn_in=10, tuning_cycles=1) -- what
+NestedSampleIt configures for the built-in sampler (nestedsample_it.py:416-427).
 
-A "step" is ONE whole converged run: initial population (Philox draw + logL), every
-batch (k-worst selection, evidence/information update, walker refill) and the final
-live-point term.  `value` = logL evaluations of the run / device time (inputs resident);
-`ms_per_step` = time-to-converged ln Z.  `e2e` = the same through the public
-`NestedSampling(...).run()` call: prior table + config go host->device, the dead-point
-log comes back device->host, inside the timed region.
+A "step" is ONE Nested Sampling batch of the running C5 run: the k worst live points die (selection,
+evidence / information update, dead-row record) and k walkers refill them, each doing 20*d tuning
++ 20*d production trial moves = 721 likelihood evaluations of 4 stiff ODE solves.  k = 800 per GPU
+(one resident wave of the walker kernel).  A converged C5 run is ~4*10^3 such steps (hours), so it is
+not a bench step; the converged-run figures carried on the same line are C2 (eggcarton, N = 10^4) and
+C3 (50-D dense Gaussian, N = 10^6) as `secondary`.
+
+`value` = likelihood evaluations actually integrated on the device (counted by the kernel; trial
+moves the prior rejects are not integrated and not counted) / device time, inputs resident.
+`e2e` = the same through the public `NestedSampling(...).run()` call on a bounded run (host priors
+and config in, dead-point table out, inside the timed region).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
@@ -29,7 +35,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="C2 eggcarton d=2 N=1e4/GPU RemainingPriorMass(1e-6)", d=2, population=10000,
+C5 = dict(name="C5 JARM ODE likelihood (synthetic JARM-shaped network: 34 species, 84 reactions, 18 sampled of 50 "
+               "parameters; 2 conditions x (pre-equilibration + 181-time solve), 5 data terms + 4 cycle terms), "
+               "N=1e5 live points, one NS batch per step",
+          population=100000, k_per_gpu=800, iterations=10, burn_in=10, tuning_cycles=1, d=18)
+
+C2 = dict(name="C2 eggcarton d=2 N=1e4/GPU RemainingPriorMass(1e-6)", d=2, population=10000,
                 iterations=50, burn_in=0, tuning_cycles=2, cutoff=1e-6, truth_logz=235.88)
 
 
@@ -92,16 +103,91 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
+
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the as-shipped restatement on host cores
+# CPU side: the SciPy stand-in for the reference's likelihood (oracle/ode.py), reference arm
 # ------------------------------------------------------------------------------------------
-def _cpu_sample(args):
-    """One bounded sample of the workload with the reference-as-shipped port; (evals, seconds)."""
+# ScipyOdeSimulator's own default solver tolerances (scipy `ode` defaults behind pysb: rtol 1e-6,
+# atol 1e-12); the parity tests use the same function at 1e-12.
+CPU_RTOL, CPU_ATOL = 1e-6, 1e-12
+
+
+def _c5_cpu_chunk(args):
+    """`n` evaluations of the JARM likelihood at prior draws with the SciPy stand-in; (evals, seconds)."""
+    seed, n = args
+    from gleipnir_b200 import jarm
+    from oracle import ode
+    like = jarm.jarm_loglikelihood()
+    desc, proto = like.network.description(), like.oracle_protocol()
+    table = jarm.jarm_prior_table()
+    rng = np.random.default_rng(seed)
+    lo = np.array([t[0] for t in table])
+    sc = np.array([t[1] for t in table])
+    Y = lo + sc * rng.uniform(size=(n, len(table)))
+    t0 = time.perf_counter()
+    try:                                    # one BLAS thread per process: the processes already fill the cores
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except ImportError:                     # pragma: no cover
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        for y in Y:
+            ode.protocol_loglike(desc, proto, y, rtol=CPU_RTOL, atol=CPU_ATOL)
+    return n, time.perf_counter() - t0
+
+
+def c5_cpu_sample(procs, n_per_proc, seed0=0):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_c5_cpu_chunk((seed0, n_per_proc))]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_c5_cpu_chunk, [(seed0 + i, n_per_proc) for i in range(procs)])
+    return sum(r[0] for r in res), time.perf_counter() - t0
+
+
+C5_CPU_SAMPLE = ("SciPy stand-in for ScipyOdeSimulator (oracle/ode.py: odeint/LSODA, analytic Jacobian, rtol %g atol %g "
+                 "= the reference solver's defaults; PySB itself is not installable here): JARM likelihood at prior "
+                 "draws, %d processes x %d evaluations per step")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path for the headline workload on all host cores.  The
+    sampler's own cost is negligible next to 4 stiff solves per evaluation, so a step is
+    a bounded batch of likelihood evaluations, one process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_per_proc = 16
+    per_step, total = [], 0
+    for i in range(args.warmup + args.steps):
+        ev, wall = c5_cpu_sample(cores, n_per_proc, seed0=1000 * i)
+        if i >= args.warmup:
+            per_step.append(wall)
+            total += ev
+    value = total / sum(per_step)
+    sample = C5_CPU_SAMPLE % (CPU_RTOL, CPU_ATOL, cores, n_per_proc)
+    line = dict(metric="logL evals/sec", value=value, unit="evals/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * float(np.mean(per_step)), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=C5["name"], sample=sample),
+                cpu_baseline=dict(value=value, unit="evals/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# C2 with the reference-as-shipped port and with the intended-algorithm oracle (BASELINE.md section 2 control)
+def _c2_shipped_sample(args):
     seed, population, max_iter = args[:3]
     import warnings
     from scipy.stats import uniform
     from oracle import reference_port as rp
-    w = WORKLOAD
+    w = C2
     np.random.seed(seed)
     pri = [uniform(loc=0.0, scale=10.0 * np.pi) for _ in range(w["d"])]
 
@@ -117,51 +203,38 @@ def _cpu_sample(args):
     return r["n_evals"], time.perf_counter() - t0
 
 
-def cpu_sample_parallel(procs, population, max_iter, seed0=0):
-    import multiprocessing as mp
+def c2_cpu_baselines(N, n_deaths):
+    """Two single-core CPU figures for C2: the reference as shipped (scipy scalar calls on every trial move)
+    and the intended algorithm with closed-form priors (oracle/engine.py) -- BASELINE.md section 2 asks for both."""
+    w = C2
+    sweeps = 20 * w["tuning_cycles"] + w["iterations"] + w["burn_in"]
+    ev1, t1 = _c2_shipped_sample((0, N, 1))
+    n_it = 300
+    ev2, t2 = _c2_shipped_sample((0, N, n_it))
+    t_iter = (t2 - t1) / (n_it - 1.0)
+    evals_full = N + (n_deaths - 1) * (1 + sweeps * w["d"])
+    full_s = t1 + (n_deaths - 1) * t_iter
+    shipped = dict(value=evals_full / full_s, unit="evals/s", cores=1, kind="port",
+                   sample="reference-as-shipped port (oracle/reference_port.py): N=%d init (%.2f s, %d evals) + %d "
+                          "iterations (%.1f s, %d evals); value = full-run evals / (t_init + (n_deaths-1)*t_iteration)"
+                          % (N, t1, ev1, n_it, t2, ev2),
+                   init_evals_per_s=ev1 / t1, iteration_evals_per_s=(ev2 - ev1) / (t2 - t1),
+                   time_to_converged_logZ_s_extrapolated=full_s)
+    from oracle import priors as pr
+    from oracle.engine import Engine
+    from oracle.likelihoods import Model
+    table = [(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * w["d"]
+    n_small, k_small = 500, 1
     t0 = time.perf_counter()
-    if procs == 1:
-        res = [_cpu_sample((seed0, population, max_iter))]
-    else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_cpu_sample, [(seed0 + i, population, max_iter) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    return sum(r[0] for r in res), wall
-
-
-def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle/reference_port.py, pinned
-    bit-for-bit to the real reference) on all host cores, one process per seed."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    w = WORKLOAD
-    cores = os.cpu_count() or 1
-    population, max_iter = w["population"], 120    # 10^4 rvs + 10^4 logL + 119 sampler calls per process
-    per_step = []
-    total_evals = 0
-    for i in range(args.warmup + args.steps):
-        ev, wall = cpu_sample_parallel(cores, population, max_iter, seed0=1000 * i)
-        if i >= args.warmup:
-            per_step.append(wall)
-            total_evals += ev
-    value = total_evals / sum(per_step)
-    n_deaths = death_count(population, w["cutoff"])
-    evals_full = population + (n_deaths - 1) * (1 + (20 * w["tuning_cycles"] + w["iterations"] + w["burn_in"]) * w["d"])
-    line = dict(metric="logL evals/sec", value=value, unit="evals/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * float(np.mean(per_step)), higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=w["name"], sample="%d processes x (N=%d init + %d iterations)" %
-                            (cores, population, max_iter)),
-                cpu_baseline=dict(value=value, unit="evals/s", cores=cores, kind="port",
-                                  sample="reference-as-shipped port (oracle/reference_port.py, bit-exact vs the "
-                                         "real reference on golden runs): %d procs x (N=%d init + %d iterations)" %
-                                         (cores, population, max_iter)),
-                e2e=dict(value=value, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                time_to_converged_logZ_s_extrapolated=evals_full / (value / cores),
-                gpu_launches=0)
-    print(json.dumps(line))
-    return 0
+    eng = Engine(table, Model("eggcarton", w["d"]), n_small, batch_k=k_small, iterations=w["iterations"],
+                 tuning_cycles=w["tuning_cycles"], seed=3)
+    eng.run(60)
+    dt = time.perf_counter() - t0
+    ev = n_small + 59 * (1 + sweeps * w["d"])
+    intended = dict(value=ev / dt, unit="evals/s", cores=1, kind="port",
+                    sample="intended algorithm, closed-form priors (oracle/engine.py, the checker of the GPU engine): "
+                           "N=%d, 60 iterations, %d evals in %.1f s" % (n_small, ev, dt))
+    return shipped, intended
 
 
 # ------------------------------------------------------------------------------------------
@@ -185,54 +258,201 @@ def measure_dfma_peak(torch, lib, L):
     return best / 1e12
 
 
-def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
+class Env(object):
+    """Process-group plumbing shared by the workloads."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        from gleipnir_b200 import _lib as L
+        self.L, self.lib = L, L.load()
+        self.comm = None
+        if self.world > 1:
+            from gleipnir_b200.sharded import get_nccl_comm
+            self.comm = get_nccl_comm()
+        self.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")     # > 126 MB L2
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(v) for v in t]
+
+
+def c5_flops_per_step(net):
+    """SURVEY 8d's algorithmic count per accepted step of an s-stage Rosenbrock method on n species and r
+    reactions: 1 Jacobian (2r*order = 4r), 1 LU (2/3 n^3), s x (RHS 3r + solve 2 n^2); RODAS4 has s = 6.
+    Also the FMAs the sparse generated code really executes per step (structural nonzeros only)."""
+    n, r, s = net.ns, len(net.reactions), 6
+    dense = 4.0 * r + 2.0 / 3.0 * n ** 3 + s * (3.0 * r + 2.0 * n * n)
+    pl = net.plan()
+    kr4 = pl.flops_executed(r)                         # counted for 4 stages (3 RHS) by odeplan
+    per_solve = (kr4 - 4.0 * r - 4.0 * 3.0 * r) / 4.0 if False else None
+    lu = 2.0 * sum(len(pl.leaf_rows[l]) * len(pl.leaf_cols[l]) for l in range(pl.nx))
+    Q = pl.filled
+    for c, cols in pl.lu_ops:
+        rows = int(Q[c + 1:pl.nc, c].sum())
+        lu += 2.0 * rows * len(cols) + rows
+    solve = 2.0 * (pl.nnz_l + pl.nnz_u + pl.nc + sum(len(a) + len(b) for a, b in zip(pl.leaf_rows, pl.leaf_cols)))
+    sparse = 4.0 * r + lu + s * (3.0 * r + solve)
+    return dense, sparse
+
+
+def run_c5(args, env):
+    """Headline: K timed NS batches of the running C5 run.  Returns the pieces of the JSON line."""
+    torch, L, world, rank = env.torch, env.L, env.world, env.rank
+    from gleipnir_b200 import jarm
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.sharded import shard_bounds
+    w = C5
+    d, N = w["d"], w["population"]
+    k = (args.batch_k if args.batch_k else w["k_per_gpu"]) * world
+    like = jarm.jarm_loglikelihood()
+    table = [(L.GL_PRIOR_UNIFORM, a, b) for a, b in jarm.jarm_prior_table()]
+    n_steps = args.warmup + args.steps
+    skw = dict(iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=2024)
+    cap = (n_steps + 2) * k
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from gleipnir_b200 import _lib as L
+        off, n_loc = shard_bounds(N, world, rank)
+        eng = DeviceEngine(table, like, n_loc, k, cap, row_offset=off, global_population=N, **skw)
+        env.comm.enable_p2p(k)
+    else:
+        eng = DeviceEngine(table, like, N, k, cap, **skw)
+    st_ = eng._stream()
+
+    def advance(total, so_far):
+        """One step of the running run: refill the waiting batch (k walkers), kill the next k worst."""
+        if world > 1:
+            L.check(eng.lib.gl_ns_step_sharded(eng._h, env.comm.h, 1, int(k), int(so_far), 0.0, st_))
+        else:
+            if so_far > 0:
+                eng.refill()
+            eng.kill(k)
+    t0 = time.perf_counter()
+    eng.init()                                              # N prior draws + N likelihood evaluations (setup, untimed)
+    advance(k, 0)                                           # first kill: from here on a step = refill + kill
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    like.counters(reset=True)
+    for i in range(args.warmup):
+        advance((i + 2) * k, (i + 1) * k)
+    env.barrier()
+    like.counters(reset=True)
+    clocks = ClockSampler(env.local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    env.barrier()
+    times = []
+    for i in range(args.warmup, n_steps):
+        env.flush.zero_()                                   # evict L2 between timed steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        advance((i + 2) * k, (i + 1) * k)
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    env.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ctr = like.counters(reset=True)
+    st = eng.state()
+    launches_per_step = w["tuning_cycles"] + 1 + 1          # walker phases + the kill / fused sharded step
+    # per-kernel time for the roofline: events around every walker launch, in 2 extra steps
+    eng.profile_enable(True)
+    for i in range(n_steps, n_steps + 2):
+        advance((i + 2) * k, (i + 1) * k)
+    torch.cuda.synchronize()
+    walk_ms, walk_launches, sel_ms, sel_launches = eng.profile_read()
+    ctr_prof = like.counters(reset=True)
+    eng.profile_enable(False)
+    t_dev = env.reduce([sum(times) * 1e-3], "MAX")[0]
+    evals, solves, steps_ode = env.reduce([ctr["evals"], ctr["solves"], ctr["steps"]], "SUM")
+    nominal_evals = args.steps * k * (1 + (20 * w["tuning_cycles"] + w["iterations"] + w["burn_in"]) * d)
+    return dict(like=like, eng=eng, k=k, N=N, t_dev=t_dev, evals=evals, solves=solves, ode_steps=steps_ode,
+                nominal_evals=nominal_evals, clocks=clk, t_init=t_init, launches=args.steps * launches_per_step * world,
+                walk_ms=walk_ms, walk_launches=walk_launches, sel_ms=sel_ms, sel_launches=sel_launches,
+                ctr_prof=ctr_prof, state=st, ms_steps=times)
+
+
+def run_c5_e2e(args, env, k):
+    """The public call, bounded: NestedSampling(...).run() with NumberOfIterations(2k) at N = 10^5 -- priors and
+    config in from the host, initial population, one refill, finalisation, the dead-point table back on the host."""
+    torch, world = env.torch, env.world
+    from gleipnir_b200 import jarm
+    from gleipnir_b200.nestedsampling import NestedSampling
+    from gleipnir_b200.nestedsampling.samplers import MetropolisComponentWiseHardNSRejection
+    from gleipnir_b200.nestedsampling.stopping_criterion import NumberOfIterations
+    w = C5
+    n_runs = max(1, min(args.steps, 2))
+    t_tot, ev_tot, rows = 0.0, 0.0, 0
+    like = jarm.jarm_loglikelihood()
+    for i in range(n_runs):
+        sps = jarm.jarm_sampled_parameters()
+        ns = NestedSampling(sps, like, w["population"], sampler=MetropolisComponentWiseHardNSRejection(
+            iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"]),
+            stopping_criterion=NumberOfIterations(2 * k), batch_k=k, seed=700 + i)
+        env.barrier()
+        like.counters(reset=True)
+        t0 = time.perf_counter()
+        ns.run()
+        torch.cuda.synchronize()
+        t_tot += time.perf_counter() - t0
+        ev_tot += like.counters(reset=True)["evals"]
+        rows = len(ns.dead_points)
+    t_max = env.reduce([t_tot], "MAX")[0]
+    ev = env.reduce([ev_tot], "SUM")[0]
+    d = w["d"]
+    return dict(value=ev / t_max, unit="evals/s", h2d_bytes_per_step=int(24 * d + ctypes.sizeof(env.L.gl_ns_config)),
+                d2h_bytes_per_step=int(rows * 8 * (d + 2) + w["population"] * d * 8 + 2 * ctypes.sizeof(env.L.gl_ns_state)),
+                ms_per_step=1e3 * t_max / n_runs, runs=n_runs,
+                call="NestedSampling(jarm priors, jarm likelihood, 1e5, sampler(10, burn 10, tc 1), NumberOfIterations(2k), "
+                     "batch_k=k).run(): initial population (1e5 evaluations) + one refilled batch + final term + "
+                     "dead_points on the host")
+
+
+def run_c2(args, env, reps):
+    """Secondary: converged C2 runs (eggcarton, N = 10^4 per GPU), device-timed; as round 1's headline."""
+    torch, L, world, rank = env.torch, env.L, env.world, env.rank
     from gleipnir_b200.engine import DeviceEngine
     from gleipnir_b200.likelihoods import EggCartonLogLikelihood
-    lib = L.load()
-    w = WORKLOAD
+    from gleipnir_b200.sharded import run_sharded_native, shard_bounds
+    w = C2
     d = w["d"]
-    N = w["population"] * world            # weak scaling: 10^4 live points per GPU, one global run
-    k = args.batch_k if args.batch_k else N // 10
+    N = w["population"] * world
+    k = N // 10
     n_deaths = death_count(N, w["cutoff"])
-    from gleipnir_b200.sharded import get_nccl_comm, run_sharded_native, shard_bounds
-    comm = get_nccl_comm() if world > 1 else None
     table = [(L.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
     like = EggCartonLogLikelihood(d)
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")     # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     def one_run(seed, profile=False):
-        skw = dict(iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0,
-                   seed=seed, walker_lanes=args.walker_lanes)
-        if world > 1:                      # one shard per rank; L* by all-gather (NCCL)
+        skw = dict(iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=seed)
+        if world > 1:
             off, n_loc = shard_bounds(N, world, rank)
-            eng = DeviceEngine(table, like, n_loc, k, n_deaths, row_offset=off, global_population=N,
-                               **skw)
+            eng = DeviceEngine(table, like, n_loc, k, n_deaths, row_offset=off, global_population=N, **skw)
         else:
             eng = DeviceEngine(table, like, N, k, n_deaths, **skw)
         if profile:
             eng.profile_enable(True)
-        flush.zero_()                      # evict L2 between timed iterations
+        env.flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if world > 1:
-            run_sharded_native(eng, comm, n_deaths, k)
+            run_sharded_native(eng, env.comm, n_deaths, k)
         else:
             eng.init()
             eng.advance(n_deaths)
@@ -240,180 +460,222 @@ def run_b200_arm(args):
         e1.record()
         e1.synchronize()
         return eng, e0.elapsed_time(e1)
-
-    for i in range(args.warmup):
+    for i in range(3):
         one_run(i)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.3)                    # let nvidia-smi deliver its first samples
-    barrier()                              # (rank 0 slept: re-align the ranks before timing)
-    times, evals, launches, logzs, errs = [], 0, 0, [], []
-    walk_ms = walk_launches = sel_ms = sel_launches = 0
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        eng, ms = one_run(100 + i, profile=False)
+    env.barrier()
+    times, evals, logzs = [], 0, []
+    for i in range(reps):
+        eng, ms = one_run(100 + i)
         st = eng.state()
         times.append(ms)
         evals += st.n_evals
-        launches += st.n_launches
         logzs.append(st.log_z)
-        errs.append(float(np.sqrt(max(st.information, 0.0) / N)))
-        last_rows = int(st.n_rows)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    # per-kernel durations for the roofline: CUDA events around every walker / selection launch.  An
-    # event record between two launches defeats their programmatic-dependent-launch overlap, so these
-    # run as extra steps of the same workload right after the timed region, not inside it.
-    prof_total_ms = 0.0
-    for i in range(min(args.steps, 3)):
-        eng, ms = one_run(100 + i, profile=True)
-        a, b, c, e = eng.profile_read()
-        walk_ms += a; walk_launches += b; sel_ms += c; sel_launches += e
-        prof_total_ms += ms
-    barrier()
+    env.barrier()
+    eng, ms = one_run(100, profile=True)
+    walk_ms, walk_launches, sel_ms, sel_launches = eng.profile_read()
+    t_dev = env.reduce([sum(times) * 1e-3], "MAX")[0]
+    ev = env.reduce([float(evals)], "SUM")[0]
+    out = dict(workload=w["name"], population_global=N, batch_k=k, n_deaths=n_deaths, runs=reps,
+               value=ev / t_dev, unit="evals/s", time_to_converged_logZ_s=t_dev / reps,
+               logZ_mean=float(np.mean(logzs)), logZ_std=float(np.std(logzs)), logZ_exact=235.85594,
+               walker_avg_launch_us=1e3 * walk_ms / max(walk_launches, 1),
+               select_avg_launch_us=1e3 * sel_ms / max(sel_launches, 1), select_share_of_step=sel_ms / ms,
+               scaling="weak (1e4 live points per GPU)")
+    if world == 1 and rank == 0 and not args.no_cpu:
+        shipped, intended = c2_cpu_baselines(N, n_deaths)
+        out["cpu_baseline_as_shipped"] = shipped
+        out["cpu_baseline_intended_algorithm"] = intended
+    return out
 
-    # ---- end-to-end through the public API (host in, host out) -----------------------------
-    from scipy.stats import uniform
-    from gleipnir_b200.nestedsampling import NestedSampling
-    from gleipnir_b200.nestedsampling.samplers import MetropolisComponentWiseHardNSRejection
-    from gleipnir_b200.nestedsampling.stopping_criterion import RemainingPriorMass
-    from gleipnir_b200.sampled_parameter import SampledParameter
 
-    def one_e2e(seed):
-        sps = [SampledParameter(i, uniform(loc=0.0, scale=10.0 * np.pi)) for i in range(d)]
-        ns = NestedSampling(sps, like, N, sampler=MetropolisComponentWiseHardNSRejection(
-            iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"]),
-            stopping_criterion=RemainingPriorMass(w["cutoff"]), batch_k=k, seed=seed)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ns.run()
-        torch.cuda.synchronize()
-        return ns, time.perf_counter() - t0
-    for i in range(min(args.warmup, 2)):
-        one_e2e(i)
-    barrier()
-    e2e_t, e2e_evals = 0.0, 0
-    for i in range(args.steps):
-        ns, t = one_e2e(500 + i)
-        e2e_t += t
-        e2e_evals += ns._n_evals / world           # sharded runs report the global count on every rank
-    barrier()
-    clk = clocks.stop() if rank == 0 else None      # sampled over both timed regions
-
-    # max over ranks (device time), sum of evals over ranks
-    dev_t = torch.tensor([sum(times) * 1e-3, e2e_t], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(evals), float(e2e_evals), float(launches)], dtype=torch.float64, device="cuda")
+def run_c3(args, env):
+    """Secondary: ONE converged C3 run (synthetic 50-D dense Gaussian, N = 10^6 in total, stop at ln X = -160):
+    strong scaling -- the live set is sharded over the ranks."""
+    torch, L, world, rank = env.torch, env.L, env.world, env.rank
+    from gleipnir_b200 import likelihoods as lk
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.sharded import shard_bounds
+    d, N = 50, 1000000
+    k = N // 10
+    n_deaths = 160 * N
+    like = lk.DenseGaussianLogLikelihood.synthetic_c3(d)
+    table = [(L.GL_PRIOR_UNIFORM, -5.0, 10.0)] * d
+    skw = dict(iterations=10, burn_in=0, tuning_cycles=1, proposal=0, seed=1)
+    # keep only the scalar outputs: the dead log of a C3-scale run is tens of GB (SURVEY 7.3)
     if world > 1:
-        dist.all_reduce(dev_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        off, n_loc = shard_bounds(N, world, rank)
+        eng = DeviceEngine(table, like, n_loc, k, 2 * k, row_offset=off, global_population=N, **skw)
+        env.comm.enable_p2p(k)
+    else:
+        eng = DeviceEngine(table, like, N, k, 2 * k, **skw)
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.init()
+    if world > 1:
+        L.check(eng.lib.gl_ns_advance_sharded(eng._h, env.comm.h, int(n_deaths), int(k), 0, 0.0, eng._stream()))
+    else:
+        eng.advance(n_deaths)
+    e1.record()
+    e1.synchronize()
+    st = eng.state()
+    t_dev = env.reduce([e0.elapsed_time(e1) * 1e-3], "MAX")[0]
+    ev = env.reduce([float(st.n_evals)], "SUM")[0]
+    return dict(workload="C3 synthetic 50-D correlated Gaussian N=1e6 (total), sampler(10, tc=1), stop at ln X = -160",
+                population_global=N, batch_k=k, n_deaths=int(st.n_dead), value=ev / t_dev, unit="evals/s",
+                time_to_converged_logZ_s=t_dev, logZ_without_final_term=st.log_z, logZ_truth=-d * float(np.log(10.0)),
+                information=st.information, scaling="strong (N fixed, sharded over the ranks)",
+                note="dead-point log not kept (tens of GB); evals = N + deaths*(1 + 30*d)")
+
+
+def run_b200_arm(args):
+    env = Env()
+    torch, L, lib, world, rank = env.torch, env.L, env.lib, env.world, env.rank
+    parity = None
+    if world > 1:
+        parity = sharded_parity_check(env)
+    c5 = run_c5(args, env)
+    e2e = run_c5_e2e(args, env, c5["k"])
+    secondary = {}
+    if not args.no_secondary:
+        secondary["C2"] = run_c2(args, env, reps=5)
+        try:
+            secondary["C3"] = run_c3(args, env)
+        except Exception as exc:                        # the headline must not die on a secondary config
+            secondary["C3"] = dict(error=str(exc)[:300])
+    env.barrier()
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            env.dist.destroy_process_group()
         return 0
-    t_dev, t_e2e = float(dev_t[0]), float(dev_t[1])
-    value = float(tot[0]) / t_dev
-    e2e_value = float(tot[1]) / t_e2e
-
-    # ---- roofline of the dominant kernel (walker) -------------------------------------------
+    value = c5["evals"] / c5["t_dev"]
+    like = c5["like"]
+    net = like.network
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     dfma_peak = measure_dfma_peak(torch, lib, L)
-    sweeps = 20 * w["tuning_cycles"] + w["iterations"] + w["burn_in"]
-    walk_evals_per_step = (k / world) * d * sweeps          # walkers of this rank (k/world on average)
-    n_walk_steps = walk_launches / (w["tuning_cycles"] + 1)
-    avg_launch_s = (walk_ms * 1e-3) / max(walk_launches, 1)
-    flop_per_eval = FLOP_PER_TRIAL_EGGCARTON_D2
-    achieved = (walk_evals_per_step / (w["tuning_cycles"] + 1)) * flop_per_eval / avg_launch_s / 1e12
-    # dependent-issue latency of DFMA: what actually bounds a Metropolis chain (one warp per walker, ~25
-    # dependent FP64 operations per round), as opposed to the pipe's throughput peak above
-    lat = ctypes.c_double(0.0)
-    lat_scratch = torch.zeros(64, dtype=torch.float64, device="cuda")
-    L.check(lib.gl_microbench_dfma_latency(4096, lat_scratch.data_ptr(), ctypes.byref(lat)))
-    hbm_peak = peaks.get("hbm_gbs")
-    walk_bytes = (k / world) * 8.0 * (2 * d + 1)        # algorithmic: seed row in, point + logL out per replacement
-    roofline = dict(kernel="walk_reg_kernel<LikeEggCarton, 2>", bound="fp64", achieved=achieved, peak=dfma_peak,
-                    unit="TFLOP/s", frac=achieved / dfma_peak if dfma_peak else None,
-                    traffic=158208, traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one production "
-                    "launch, ncu --set full (profiles/r01_g_walk_reg_kernel_c2.txt); algorithmic bytes per launch: "
-                    "%d" % int(walk_bytes),
+    dense_flop, sparse_flop = c5_flops_per_step(net)
+    # roofline of the dominant kernel from the 2 profiled steps on this rank: ODE steps integrated inside the
+    # walker launches / the CUDA-event time of those launches
+    walk_s = c5["walk_ms"] * 1e-3
+    steps_prof = c5["ctr_prof"]["steps"]
+    achieved = steps_prof * dense_flop / walk_s / 1e12 if walk_s > 0 else None
+    step_ms = float(np.mean(c5["ms_steps"]))
+    roofline = dict(kernel="walk_coop_kernel<Net=jarm> (RODAS4, one system per warp, one warp per condition)",
+                    bound="fp64", achieved=achieved, peak=dfma_peak, unit="TFLOP/s",
+                    frac=(achieved / dfma_peak) if achieved and dfma_peak else None, traffic=None,
+                    traffic_source="not re-measured in this run; ncu --set full of the same kernel family: "
+                                   "profiles/r02_b_jarm_eval.txt (dram bytes are ~1e-5 of the HBM roof: the state lives in "
+                                   "registers and shared memory)",
                     peak_source="gl_microbench_dfma measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    flop_per_trial_move=flop_per_eval,
-                    dependent_dfma_latency_cycles=lat.value,
-                    note="latency-bound by construction: a Metropolis chain is one dependent sequence and C2 offers "
-                         "k*G = 32 000 threads to a 303 000-thread machine; neither HBM nor a tensor pipe is the limiter",
-                    walker_hbm=dict(bound="hbm", achieved=walk_bytes / avg_launch_s / 1e9, peak=hbm_peak, unit="GB/s",
-                                    frac=(walk_bytes / avg_launch_s / 1e9 / hbm_peak) if hbm_peak else None),
-                    avg_launch_us=avg_launch_s * 1e6, launches_timed=int(walk_launches),
-                    walker_share_of_step=walk_ms / prof_total_ms, select_share_of_step=sel_ms / prof_total_ms,
-                    timing="CUDA events around every launch in %d extra steps after the timed region "
-                           "(%.3f ms/step with the events in place)" % (min(args.steps, 3), prof_total_ms / min(args.steps, 3)),
-                    select_avg_launch_us=1e3 * sel_ms / max(sel_launches, 1),
-                    select_hbm=dict(bound="hbm", achieved=((8.0 * N / world) / (1e-3 * sel_ms / sel_launches) / 1e9)
-                                    if sel_ms > 0 and sel_launches else None,
-                                    peak=peaks.get("hbm_gbs"), unit="GB/s"))
-    # ---- CPU baseline: bounded sample on one host core ---------------------------------------
-    # init (N rvs + N logL) and the per-iteration sampler cost are timed separately so that the
-    # extrapolation to the full run is t_init + (n_deaths - 1) * t_iteration
+                    algorithmic_flop_per_ode_step=dense_flop,
+                    algorithmic_flop_formula="SURVEY 8d: 4r + 2/3 n^3 + s(3r + 2n^2), n=34 species, r=84 reactions, s=6 stages",
+                    executed_sparse_flop_per_ode_step=sparse_flop,
+                    executed_sparse_tflops=(steps_prof * sparse_flop / walk_s / 1e12) if walk_s > 0 else None,
+                    ode_steps_per_s=steps_prof / walk_s if walk_s > 0 else None,
+                    ode_steps_per_solve=c5["ode_steps"] / max(c5["solves"], 1),
+                    solves_per_eval=c5["solves"] / max(c5["evals"], 1),
+                    rhs_evals_per_s=6.0 * steps_prof / walk_s if walk_s > 0 else None,
+                    avg_launch_ms=c5["walk_ms"] / max(c5["walk_launches"], 1), launches_timed=int(c5["walk_launches"]),
+                    walker_share_of_step=c5["walk_ms"] / 2.0 / step_ms,
+                    select_avg_launch_us=1e3 * c5["sel_ms"] / max(c5["sel_launches"], 1),
+                    timing="CUDA events around every walker launch in 2 extra steps after the timed region",
+                    note="latency-bound: a walker is a chain of 721 dependent likelihood evaluations, each 2 x (pre-equilibration "
+                         "+ main) stiff solves of ~10^2-10^3 dependent Rosenbrock steps; fp64 pipe utilisation and stall "
+                         "reasons from ncu are in profiles/r02_*")
     cpu = None
-    if world == 1:
-        ev1, t1 = cpu_sample_parallel(1, N, 1)
-        n_it = 600                                  # ~12 s of host work on one core
-        cpu_evals, cpu_wall = cpu_sample_parallel(1, N, n_it)
-        t_iter = (cpu_wall - t1) / (n_it - 1.0)
-        evals_full = N + (n_deaths - 1) * (1 + sweeps * d)
-        cpu_full_s = t1 + (n_deaths - 1) * t_iter
-        cpu_value = evals_full / cpu_full_s
-        cpu = dict(value=cpu_value, unit="evals/s", cores=1, kind="port",
-                   sample="reference-as-shipped port (oracle/reference_port.py), N=%d init (%.2f s) + "
-                          "%d iterations (%d evals, %.1f s); value = full-run evals / (t_init + "
-                          "(n_deaths-1)*t_iteration)" % (N, t1, n_it, cpu_evals, cpu_wall),
-                   time_to_converged_logZ_s_extrapolated=cpu_full_s)
+    if world == 1 and not args.no_cpu:
+        ev, wall = c5_cpu_sample(1, 400)
+        cpu = dict(value=ev / wall, unit="evals/s", cores=1, kind="port",
+                   sample=C5_CPU_SAMPLE % (CPU_RTOL, CPU_ATOL, 1, 400) + " (%.1f s)" % wall)
+    w = C5
     line = dict(metric="logL evals/sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
+                warmup=args.warmup, ms_per_step=1e3 * c5["t_dev"] / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=w["name"], population_per_gpu=w["population"], population_global=N, batch_k=k, n_deaths=n_deaths,
-                            walker_lanes=args.walker_lanes or "auto",
-                            sampler="MetropolisComponentWiseHardNSRejection(iterations=50, tuning_cycles=2)",
-                            l2="flushed between timed runs (256 MB memset)",
-                            parallelism=("live set sharded over %d ranks; per step one fused kernel exchanges "
-                                         "~k/world + 8 sigma candidate logL per rank over NVLink peer memory" % world)
+                config=dict(workload=w["name"], population_global=c5["N"], batch_k=c5["k"], walkers_per_gpu_per_step=c5["k"] // world,
+                            sampler="MetropolisComponentWiseHardNSRejection(iterations=10, burn_in=10, tuning_cycles=1)",
+                            ode="RODAS4, rtol %g atol %g" % (like.rtol, like.atol),
+                            evals_counted="integrated on the device (kernel counter); the reference's own count, which "
+                                          "includes trial moves rejected by the prior alone, is nominal_evals",
+                            nominal_evals=c5["nominal_evals"], init_s=c5["t_init"],
+                            l2="flushed between timed steps (256 MB memset)",
+                            parallelism=("live set sharded over %d ranks (N/world each); per step one fused kernel exchanges the "
+                                         "candidate logL over NVLink peer memory; k = 800 walkers per GPU (weak in k)" % world)
                             if world > 1 else "single"),
-                clocks=clk, gpu_launches=int(float(tot[2])),
-                e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int(24 * d + ctypes.sizeof(L.gl_ns_config)),
-                         # dead-point table + final live points + two state snapshots
-                         d2h_bytes_per_step=int(last_rows * world * 8 * (d + 2) + N * d * 8 + 2 * ctypes.sizeof(L.gl_ns_state)),
-                         ms_per_step=1e3 * t_e2e / args.steps),
-                roofline=roofline,
-                cpu_baseline=cpu,
-                time_to_converged_logZ_s=t_dev / args.steps,
-                logZ_mean=float(np.mean(logzs)), logZ_std=float(np.std(logzs)), logZ_err_reported=float(np.mean(errs)),
-                logZ_truth=w["truth_logz"])
+                clocks=c5["clocks"], gpu_launches=int(c5["launches"]), e2e=e2e, roofline=roofline, cpu_baseline=cpu,
+                time_to_converged_logZ_s=None,
+                time_to_converged_note="a converged C5 run at N=1e5 is ~N*(H + ln(1/X_stop))/k batches (hours on one GPU) "
+                                       "and is not measured here; converged runs: secondary.C2, secondary.C3",
+                secondary=secondary)
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
     return 0
 
 
-# fp64 operations per trial move of walk_kernel<LikeEggCarton>, d=2 (DESIGN.md "Roofline"):
-# ncu instruction mix of the r01 baseline capture (profiles/r01_a_walk_kernel_c2_baseline.txt):
-# 57 DFMA + 14 DMUL + 5 DADD per trial move = 2*57 + 14 + 5 = 133 flop (2 cos, 2 prior pdfs,
-# ratio, proposal, (2+chi)^5, u52 conversions).
-FLOP_PER_TRIAL_EGGCARTON_D2 = 133.0
+def sharded_parity_check(env):
+    """world > 1 only (the driver's GPU test box has one GPU): before timing, the fused peer-memory step, the NCCL
+    all-gather path and the CPU oracle of the sharded algorithm (oracle/sharded.py, every rank's shard run through
+    the same SPMD protocol) on a small eggcarton run -- this rank's dead rows compared slot for slot."""
+    L, world, rank = env.L, env.world, env.rank
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.likelihoods import EggCartonLogLikelihood
+    from gleipnir_b200.sharded import LocalComm, run_sharded, run_sharded_native, shard_bounds
+    from oracle import priors as pr
+    from oracle.likelihoods import Model
+    from oracle.sharded import OracleShard
+    d, N, k, n_deaths, seed = 2, 4000, 400, 2400, 17
+    table = [(L.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d
+    like = EggCartonLogLikelihood(d)
+    off, n_loc = shard_bounds(N, world, rank)
+    res = {}
+    for mode in ("nccl", "p2p"):                       # NCCL first: the peer mapping, once made, stays in use
+        if mode == "nccl":
+            os.environ["GLEIPNIR_B200_NO_P2P"] = "1"
+        else:
+            os.environ.pop("GLEIPNIR_B200_NO_P2P", None)
+        eng = DeviceEngine(table, like, n_loc, k, n_deaths, row_offset=off, global_population=N, iterations=4,
+                           tuning_cycles=1, seed=seed)
+        run_sharded_native(eng, env.comm, n_deaths, k, candidate_sigmas=0.0)
+        tab, idx, step = eng.dead_table()
+        res[mode] = (tab, idx, step, eng.state().log_z, bool(env.lib.gl_comm_p2p_ready(env.comm.h)))
+    same = bool(np.array_equal(res["p2p"][0], res["nccl"][0]) and np.array_equal(res["p2p"][1], res["nccl"][1]))
+    ora = []
+    for rk in range(world):
+        o, nl = shard_bounds(N, world, rk)
+        ora.append(OracleShard([(pr.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * d, Model("eggcarton", d), nl, batch_k=k,
+                               seed=seed, row_offset=o, global_population=N, iterations=4, tuning_cycles=1))
+    run_sharded(ora, LocalComm(world), n_deaths, k, candidate_sigmas=0.0)
+    want = ora[rank].result
+    tab, idx, step = res["p2p"][:3]
+    nd = len(want["dead_index"])
+    od = np.lexsort((idx[:nd], step[:nd]))
+    oo = np.lexsort((want["dead_index"], want["dead_batch"]))
+    ok_oracle = bool(np.array_equal(idx[:nd][od], want["dead_index"][oo]) and
+                     np.allclose(tab[:nd][od], want["dead"][:nd][oo], rtol=1e-12, atol=1e-13) and
+                     abs(res["p2p"][3] - want["logZ"]) <= 1e-12 * abs(want["logZ"]))
+    flags = env.reduce([1.0 if same else 0.0, 1.0 if ok_oracle else 0.0, 1.0 if res["p2p"][4] else 0.0,
+                        0.0 if res["nccl"][4] else 1.0], "MIN")
+    return dict(config="eggcarton N=%d k=%d deaths=%d world=%d, full exchange" % (N, k, n_deaths, world),
+                peer_memory_equals_nccl_path_bitwise=bool(flags[0]), equals_cpu_oracle_shards=bool(flags[1]),
+                peer_memory_path_ran=bool(flags[2]), nccl_path_ran=bool(flags[3]), logZ=res["p2p"][3],
+                tolerance="slots identical, values 1e-12 relative")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-k", type=int, default=0)
-    ap.add_argument("--walker-lanes", type=int, default=0, help="lanes per walker (0 = auto)")
+    ap.add_argument("--batch-k", type=int, default=0, help="C5 walkers per GPU per step (default 800)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 secondary configs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -216,8 +216,31 @@ int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev,
 
 // Enqueue the sharded run until `n_deaths_total` GLOBAL deaths: per step candidates -> NCCL
 // all-gather -> commit -> refill, all on `stream`.
+}  // extern "C"
+
+// `open_ended`: every batch of this call will be refilled by a later call (stepping a long run batch by batch);
+// otherwise the batch that reaches n_deaths_total is the run's last and is left for the final term.
+static int advance_sharded_impl(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
+                                double candidate_sigmas, bool open_ended, void *stream);
+
+extern "C" {
+
 int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
                           double candidate_sigmas, void *stream) {
+    return advance_sharded_impl(ns, c, n_deaths_total, batch_k, n_dead_so_far, candidate_sigmas, false, stream);
+}
+
+int gl_ns_step_sharded(gl_ns *ns, gl_comm *c, int32_t n_batches, int32_t batch_k, int64_t n_dead_so_far,
+                       double candidate_sigmas, void *stream) {
+    GL_REQUIRE(n_batches >= 1, "n_batches must be >= 1");
+    return advance_sharded_impl(ns, c, n_dead_so_far + (int64_t)n_batches * batch_k, batch_k, n_dead_so_far,
+                                candidate_sigmas, true, stream);
+}
+
+}  // extern "C"
+
+static int advance_sharded_impl(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
+                                double candidate_sigmas, bool open_ended, void *stream) {
     GL_REQUIRE(ns != nullptr && c != nullptr, "NULL argument");
     GL_REQUIRE(batch_k >= 1, "batch_k must be >= 1");
     int rc = gl::comm_reserve(c, (size_t)(batch_k > 4 ? batch_k : 4));
@@ -239,7 +262,7 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
         }
         first = false;
         const int32_t m = gl_ns_shard_candidate_count(k, c->world, n_local, candidate_sigmas);
-        gl_ns_internal_commit_refills(ns, done + k < n_deaths_total ? 1 : 0);
+        gl_ns_internal_commit_refills(ns, (open_ended || done + k < n_deaths_total) ? 1 : 0);
         if (c->p2p_ready && m <= c->tables.cap && n_local <= 196608 && (int64_t)c->world * m <= 196608) {
             // fused step: candidates, exchange over NVLink peer memory and commit in ONE launch
             c->epoch += 1;
@@ -258,6 +281,8 @@ int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t
     }
     return GL_OK;
 }
+
+extern "C" {
 
 int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream) {
     GL_REQUIRE(ns != nullptr && c != nullptr, "NULL argument");

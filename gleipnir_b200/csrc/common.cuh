@@ -50,13 +50,13 @@ inline int cuda_fail(cudaError_t e, const char *what, const char *file, int line
         }                                                                   \
     } while (0)
 
-inline int sm_count() {   // cached; 148 on B200
-    static int cached = 0;
-    if (cached > 0) return cached;
+inline int sm_count() {   // of the current device, cached per device; 148 on B200
+    static int cached[64] = {0};
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cached[dev & 63] > 0) return cached[dev & 63];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    cached[dev & 63] = n;
     return n;
 }
 

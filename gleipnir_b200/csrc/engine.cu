@@ -7,6 +7,7 @@
 //            -> walkers (tuning_cycles + 1 launches, walker.cu) -> end_walk
 #include <new>
 #include <vector>
+#include <stdlib.h>
 #include "engine.cuh"
 #include "philox.cuh"
 #include <cooperative_groups.h>
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(1024) accumulate_kernel(EngineState *S, const 
         S->n_dead += k;
         if (S->n_rows + k_rows <= capacity) S->n_rows += k_rows;
         S->lstar = key_to_double(mk);
-        S->do_walk = S->n_dead < n_target;
+        S->do_walk = 1;       // whether a refill follows is the host's call: a run driven in slices refills this batch in its NEXT gl_ns_advance
     }
 }
 
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) shard_local_kernel(EngineState *S, const 
                                                           long long *__restrict__ dead_list,
                                                           unsigned char *__restrict__ is_dead) {
     __shared__ int s_start, s_end;
-    if (m < k && threadIdx.x < world && shard_exchange_overflowed(positions, k, m, threadIdx.x)) S->shard_overflow = 1;
+    if (m < k && threadIdx.x < world && shard_exchange_overflowed(positions, k, m, threadIdx.x)) atomicMax(&S->shard_overflow, 1);
     if (threadIdx.x == 0) {
         const long long lo_pos = (long long)rank * m, hi_pos = lo_pos + m;
         int a = 0, b = k;                          // lower_bound(positions, lo_pos)
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(KILL_SMALL_THREADS) kill_small_kernel(
         S->n_dead += k;
         if (room) S->n_rows += k;
         S->lstar = key_to_double(kstar);
-        S->do_walk = S->n_dead < n_target;
+        S->do_walk = 1;       // whether a refill follows is the host's call: a run driven in slices refills this batch in its NEXT gl_ns_advance
     }
 }
 
@@ -1090,7 +1091,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) ki
             if (room) S->n_rows = base_row + k;
             S->lstar = key_to_double(kstar);
             S->k_cur = k;
-            S->do_walk = n_dead0 + k < n_target;
+            S->do_walk = 1;   // (the host decides whether a refill follows: see accumulate_kernel)
             if (end_walk_tc >= 0) {
                 S->n_evals += (unsigned long long)((long long)kp * evals_per_walker);
                 S->step = step_now;
@@ -1185,7 +1186,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     __syncthreads();
     const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, n, k, positions, nullptr);
     shard_rank_bounds(positions, k, m, world, s_bound);          // every rank's contiguous share of `positions`
-    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) S->shard_overflow = 1;
+    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) atomicMax(&S->shard_overflow, 1);
     const int start = s_bound[rank], n_own = s_bound[rank + 1] - s_bound[rank];
     const double logw = logX0 - log(n_global + 1.0);
     const double w = exp(logw);
@@ -1263,6 +1264,23 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Watchdog of the peer-memory arrival wait, in ns: GLEIPNIR_PEER_TIMEOUT_S seconds (default 600 -- the wait
+// includes the other ranks' walker time of the step, which is tens of seconds for ODE likelihoods).
+static unsigned long long peer_timeout_ns_host() {
+    static unsigned long long cached = 0;
+    if (!cached) {
+        const char *e = getenv("GLEIPNIR_PEER_TIMEOUT_S");
+        double s = e ? atof(e) : 600.0;
+        if (!(s > 0.0)) s = 600.0;
+        cached = (unsigned long long)(s * 1e9);
+    }
+    return cached;
+}
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1275,7 +1293,8 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     long long *__restrict__ cand_list, long long *__restrict__ positions, const double *__restrict__ live,
     const double *__restrict__ logl, long long *__restrict__ dead_list, unsigned char *__restrict__ is_dead,
     double *__restrict__ dead_x, double *__restrict__ dead_logl, double *__restrict__ dead_w,
-    long long *__restrict__ dead_idx, int *__restrict__ dead_step, int defer_book) {
+    long long *__restrict__ dead_idx, int *__restrict__ dead_step, int defer_book,
+    unsigned long long peer_timeout_ns) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();
@@ -1321,13 +1340,15 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     if (c == 0 && tid < world) {
         st_release_sys(T.flags[tid] + rank, epoch);               // "rank's candidates of this epoch are in your buffer"
         const unsigned int *mine = T.flags[rank] + tid;
-        const long long t0 = clock64();
+        // wall-clock watchdog (%globaltimer, ns): the wait also absorbs the ranks' walker skew, which is
+        // seconds for ODE likelihoods, so the limit is generous and configurable (GLEIPNIR_PEER_TIMEOUT_S)
+        const unsigned long long t0 = global_timer_ns();
         int timeout = 0;
         while ((int)(ld_acquire_sys(mine) - epoch) < 0) {         // flags only grow (wrap-safe compare)
             __nanosleep(40);
-            if (clock64() - t0 > 20000000000LL) { timeout = 1; break; }    // ~10 s: a peer died
+            if (global_timer_ns() - t0 > peer_timeout_ns) { timeout = 1; break; }    // a peer died
         }
-        if (timeout) S->shard_overflow = 2;
+        if (timeout) atomicMax(&S->shard_overflow, 2);            // sticky and never downgraded to 1
     }
     cluster.sync();
     // ---- global selection on what arrived ------------------------------------------------------------------
@@ -1342,7 +1363,7 @@ __global__ void __cluster_dims__(KC_CTAS, 1, 1) __launch_bounds__(KC_THREADS) sh
     }
     const unsigned long long kstar = cluster_select_kworst(cluster, sm, keys, n, k, positions, nullptr);
     shard_rank_bounds(positions, k, m, world, s_bound);          // every rank's contiguous share of `positions`
-    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) S->shard_overflow = 1;
+    if (c == 0 && m < k && tid < world && s_bound[tid + 1] - s_bound[tid] >= m) atomicMax(&S->shard_overflow, 1);
     const int start = s_bound[rank], n_own = s_bound[rank + 1] - s_bound[rank];
     const double logw = logX0 - log(n_global + 1.0);
     const double w = exp(logw);
@@ -2491,7 +2512,8 @@ int gl_ns_internal_shard_step_p2p(gl_ns *ns, const gl::PeerTables *tables, int32
                            tc_arg, epw, (int)N, m, world, rank, k, ns->d, ns->cfg.row_offset, n_global,
                            ns->cfg.dead_capacity, *tables, epoch, ns->cand_list, ns->positions, ns->buf.live,
                            ns->buf.logl, ns->dead_list, ns->is_dead, ns->buf.dead_x, ns->buf.dead_logl, ns->buf.dead_w,
-                           (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0));
+                           (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0,
+                           gl::peer_timeout_ns_host()));
     gl::prof_mark(ns, ns->ev_sel, st);
     ns->prof_sel_launches += 1;
     ns->h_launches += 1;

@@ -121,7 +121,15 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkParams P, ModelD
         const uint32_t c2_base = (uint32_t)((tuning ? phase * 20 : P.tuning_cycles * 20) * d);
         const bool normal = P.proposal == GL_PROPOSAL_NORMAL;
         int m = 0, base = -CH;                     // ring holds moves [base, base+CH)
+        // functors that track their value incrementally (dense Gaussian: O(1) update of the quadratic form)
+        // recompute it exactly every RESYNC_SWEEPS sweeps, so rounding drift cannot accumulate over a chain
+        constexpr int RESYNC = resync_sweeps<Like>::value;
+        int next_resync = RESYNC > 0 ? RESYNC * d : 0x7fffffff;
         while (m < n_moves) {                      // group-uniform
+            if (RESYNC > 0 && m >= next_resync) {
+                L = like.refresh(x, c, WPB, lane, G, gmask, L);
+                next_resync += RESYNC * d;
+            }
             if (m + G > base + CH) {
                 // refill: everything about moves [m, m+CH) that does not depend on the walker's
                 // state -- Philox block, proposal step r*w (or ndtri(r)*w), acceptance uniform.
@@ -579,7 +587,10 @@ struct WalkLauncher {
             smem = walker_smem_bytes(P.d, Like::cache_size(P.d), G);
         }
         GL_REQUIRE(smem <= 227 * 1024, "walker state does not fit in shared memory (d=%d)", P.d);
-        static thread_local int configured_smem = 0;
+        static thread_local int configured[64] = {0};      // per device: function attributes belong to a device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &configured_smem = configured[dev & 63];
         if (smem > 48 * 1024 && smem > configured_smem) {
             GL_CUDA(cudaFuncSetAttribute(walk_kernel<Like, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             GL_CUDA(cudaFuncSetAttribute(walk_kernel<Like, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -16,6 +16,18 @@ def _torch():
     return torch
 
 
+def _on_device(fn):
+    """Run a DeviceEngine method with the engine's device current: the C library launches on the current
+    device (kernels, cudaMalloc of model data, peer buffers), so `device='cuda:1'` must make it current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with _torch().cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class DeviceEngine(object):
     """One device-resident NS run: live set, dead-point log, accumulators, widths.
 
@@ -32,7 +44,15 @@ class DeviceEngine(object):
             model_handle = model_handle.device_model()
         self.d = len(prior_table)
         self.N = int(population_size)
-        self.device = torch.device("cuda" if device is None else device)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self._construct(torch, prior_table, model_handle, batch_k, n_deaths_capacity, iterations, burn_in,
+                            tuning_cycles, proposal, seed, walker_lanes, row_offset, global_population)
+
+    def _construct(self, torch, prior_table, model_handle, batch_k, n_deaths_capacity, iterations, burn_in,
+                   tuning_cycles, proposal, seed, walker_lanes, row_offset, global_population):
         cap = int(n_deaths_capacity) + self.N
         self.cfg = _lib.gl_ns_config(population_size=self.N, batch_k=int(batch_k), iterations=int(iterations),
                                      burn_in=int(burn_in), tuning_cycles=int(tuning_cycles),
@@ -70,6 +90,7 @@ class DeviceEngine(object):
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
 
+    @_on_device
     def init(self, live=None, logl=None):
         """Draw + evaluate the initial population (or adopt a caller-supplied one)."""
         torch = _torch()
@@ -80,15 +101,19 @@ class DeviceEngine(object):
             skip = 1
         _lib.check(self.lib.gl_ns_init(self._h, skip, self._stream()))
 
+    @_on_device
     def advance(self, n_deaths_total):
         _lib.check(self.lib.gl_ns_advance(self._h, int(n_deaths_total), self._stream()))
 
+    @_on_device
     def kill(self, k):
         _lib.check(self.lib.gl_ns_kill(self._h, int(k), self._stream()))
 
+    @_on_device
     def refill(self):
         _lib.check(self.lib.gl_ns_refill(self._h, self._stream()))
 
+    @_on_device
     def inject(self, points, logls):
         torch = _torch()
         p = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64)).to(self.device)
@@ -96,6 +121,7 @@ class DeviceEngine(object):
         _lib.check(self.lib.gl_ns_inject(self._h, p.data_ptr(), l.data_ptr(), int(l.numel()), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()     # p, l must outlive the kernels
 
+    @_on_device
     def finalize(self):
         _lib.check(self.lib.gl_ns_finalize(self._h, self._stream()))
 
@@ -107,12 +133,14 @@ class DeviceEngine(object):
         _lib.check(self.lib.gl_ns_force_multipass_select(self._h, 1 if enable else 0))
 
     # ---- sharded run (one engine per rank; see gleipnir_b200/sharded.py) ---------------------
+    @_on_device
     def candidates(self, k):
         torch = _torch()
         out = torch.empty(int(k), dtype=torch.float64, device=self.device)
         _lib.check(self.lib.gl_ns_shard_candidates(self._h, int(k), out.data_ptr(), self._stream()))
         return out
 
+    @_on_device
     def commit(self, gathered, world, rank, k):
         """`gathered` holds m = len/world candidates per rank (m <= k: truncated exchange)."""
         self._gathered = gathered                       # must outlive the enqueued kernels
@@ -134,12 +162,14 @@ class DeviceEngine(object):
             raise RuntimeError("sharded run: a peer did not deliver its candidates within 10 s (peer-memory exchange)")
         return bool(flag)
 
+    @_on_device
     def final_partial(self):
         torch = _torch()
         out = torch.empty(4, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.gl_ns_shard_final_partial(self._h, out.data_ptr(), self._stream()))
         return out
 
+    @_on_device
     def finalize_sharded(self, gathered, world, rank):
         self._gathered = gathered
         _lib.check(self.lib.gl_ns_shard_finalize(self._h, gathered.data_ptr(), int(world), int(rank), self._stream()))
@@ -151,6 +181,7 @@ class DeviceEngine(object):
     def profile_enable(self, enable=True):
         _lib.check(self.lib.gl_ns_profile_enable(self._h, 1 if enable else 0))
 
+    @_on_device
     def profile_read(self):
         """(walk_ms, walk_launches, select_ms, select_launches) from CUDA events recorded on the
         launching stream around the walker / selection kernels."""
@@ -160,11 +191,13 @@ class DeviceEngine(object):
                                                ctypes.byref(sl)))
         return wm.value, wl.value, sm_.value, sl.value
 
+    @_on_device
     def state(self):
         st = _lib.gl_ns_state()
         _lib.check(self.lib.gl_ns_read_state(self._h, ctypes.byref(st), self._stream()))
         return st
 
+    @_on_device
     def dead_table_device(self):
         """`dead_points` values assembled and ordered on the device (gl_ns_export_dead):
         host array [rows, d+2] in death order after ONE device->host copy.  Batches larger than
@@ -181,6 +214,7 @@ class DeviceEngine(object):
         torch.cuda.current_stream(self.device).synchronize()
         return host.numpy()
 
+    @_on_device
     def dead_table(self):
         """Dead-point log as a host array [rows, d+2] (log_l, weight, x...) in death order,
         plus the slot index and batch id of every row."""

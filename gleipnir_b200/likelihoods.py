@@ -14,6 +14,14 @@ import numpy as np
 from . import _lib
 
 
+def _current_device():
+    try:
+        import torch
+        return torch.cuda.current_device() if torch.cuda.is_available() else None
+    except ImportError:          # pragma: no cover
+        return None
+
+
 class DeviceLogLikelihood(object):
     """Base class: owns a ``gl_model`` handle created lazily on first use."""
 
@@ -26,9 +34,15 @@ class DeviceLogLikelihood(object):
         raise NotImplementedError
 
     def device_model(self):
+        """The model's device data (dense matrices, ODE blobs) lives on the device that is current at the
+        first use; using the object from another device is an error, not a silent cross-device access."""
         if self._handle is None:
             lib = _lib.load()
             self._handle = self._create(lib)
+            self._device_index = _current_device()
+        elif getattr(self, "_device_index", None) not in (None, _current_device()):
+            raise _lib.GleipnirB200Error("this likelihood object was created on cuda:%s and is being used with cuda:%s "
+                                         "current" % (self._device_index, _current_device()))
         return self._handle
 
     def __del__(self):
@@ -49,10 +63,12 @@ class DeviceLogLikelihood(object):
         except ImportError:          # pragma: no cover
             is_tensor = False
         if is_tensor:
-            xt = x.to(dtype=torch.float64, device="cuda").contiguous().reshape(-1, self.ndim)
-            out = torch.empty(xt.shape[0], dtype=torch.float64, device="cuda")
-            _lib.check(lib.gl_loglike_eval(self.device_model(), xt.data_ptr(), xt.shape[0], out.data_ptr(),
-                                           torch.cuda.current_stream().cuda_stream))
+            dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            with torch.cuda.device(dev):
+                xt = x.to(dtype=torch.float64, device=dev).contiguous().reshape(-1, self.ndim)
+                out = torch.empty(xt.shape[0], dtype=torch.float64, device=dev)
+                _lib.check(lib.gl_loglike_eval(self.device_model(), xt.data_ptr(), xt.shape[0], out.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
             return out
         xa = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, self.ndim))
         out = np.empty(xa.shape[0], dtype=np.float64)

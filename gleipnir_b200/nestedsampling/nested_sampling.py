@@ -74,6 +74,27 @@ class NestedSampling(NestedSamplingBase):
         self._engine = None
         self._state = None
 
+    @classmethod
+    def from_dead_points(cls, sampled_parameters, loglikelihood, population_size, dead_points, log_evidence,
+                         information=0.0, device=None):
+        """A finished run rebuilt from its dead-point table (``dead_points`` of this class or of upstream Gleipnir:
+        columns log_l, weight, parameters): every post-processing output -- ``posteriors``, ``max_loglikelihood``,
+        ``akaike_ic``, ``bayesian_ic``, ``deviance_ic``, ``best_fit_*`` (nested_sampling.py:266-336,
+        nsbase.py:93-175) -- then works on it without re-running."""
+        ns = cls(sampled_parameters, loglikelihood, population_size, device=device)
+        vals = dead_points.to_numpy(dtype=float) if hasattr(dead_points, "to_numpy") else np.asarray(dead_points, dtype=float)
+        if vals.ndim != 2 or vals.shape[1] != len(sampled_parameters) + 2:
+            raise ValueError("dead_points must be [rows, 2 + number of sampled parameters]")
+        ns._dead_values = np.ascontiguousarray(vals, dtype=np.float64)
+        ns._log_evidence = float(log_evidence)
+        with np.errstate(over="ignore"):
+            ns._evidence = float(np.exp(log_evidence))
+        ns._information = float(information)
+        ns._logZ_err = float(np.sqrt(max(ns._information, 0.0) / population_size))
+        ns._evidence_error = float(np.exp(ns._logZ_err))
+        ns._dead_points = None
+        return ns
+
     # ------------------------------------------------------------------------------------
     def _resolve_batch_k(self):
         n = int(self.population_size)
@@ -104,14 +125,17 @@ class NestedSampling(NestedSamplingBase):
             raise RuntimeError("sharded=True needs an initialised torch.distributed group with world_size > 1")
         return None
 
-    def _run_sharded(self, dist, loglike, table, n, k, seed, scfg, n_deaths, verbose):
-        """One shard per rank, global threshold by all-gather (gleipnir_b200/sharded.py)."""
+    def _run_sharded(self, dist, loglike, table, n, k, seed, scfg, n_deaths, verbose, chunked=False):
+        """One shard per rank, global threshold by all-gather (gleipnir_b200/sharded.py).  ``chunked``: a user-defined
+        stopping criterion, evaluated by every rank on the (identical) run state after every batch; ``n_deaths`` is
+        then the capacity of the dead-point log."""
         import torch
         from ..sharded import (gather_dead_table_device, gather_dead_tables, get_nccl_comm, run_sharded_native,
-                               shard_bounds)
+                               run_sharded_sliced, shard_bounds)
         comm = get_nccl_comm()
         rank = comm.rank
-        seed_t = torch.tensor([seed], dtype=torch.int64, device="cuda")
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        seed_t = torch.tensor([seed], dtype=torch.int64, device=dev)
         dist.broadcast(seed_t, 0)                       # every rank must use rank 0's Philox key
         off, n_loc = shard_bounds(n, comm.world, rank)
         if k >= n_loc:
@@ -119,7 +143,15 @@ class NestedSampling(NestedSamplingBase):
         eng = DeviceEngine(table, loglike, n_loc, k, n_deaths, seed=int(seed_t.item()),
                            device=self.device, row_offset=off, global_population=n, **scfg)
         self._engine = eng
-        run_sharded_native(eng, comm, n_deaths, k)
+        if chunked:
+            def should_stop(state):
+                self._n_iterations = int(state.n_dead)
+                self._evidence = float(np.exp(state.log_z))
+                self._information = float(state.information)
+                return bool(self._stopping_criterion())
+            n_deaths = run_sharded_sliced(eng, comm, k, n_deaths, should_stop)
+        else:
+            run_sharded_native(eng, comm, n_deaths, k)
         st = eng.state()
         if k <= 8192:
             table_rows = gather_dead_table_device(eng, k, n_deaths)     # ordered on the device
@@ -127,7 +159,7 @@ class NestedSampling(NestedSamplingBase):
             rows, idx, step = gather_dead_tables(eng)
             from ..engine import death_order
             table_rows = rows[death_order(rows[:, 0], idx, step)]
-        evals = torch.tensor([st.n_evals], dtype=torch.int64, device="cuda")
+        evals = torch.tensor([st.n_evals], dtype=torch.int64, device=eng.device)
         dist.all_reduce(evals)
         live = torch.empty((n, eng.d), dtype=torch.float64, device=eng.device)
         dist.all_gather_into_tensor(live, eng.live)
@@ -154,10 +186,8 @@ class NestedSampling(NestedSamplingBase):
             capacity = n_deaths
         dist = self._dist_world()
         if dist is not None:
-            if chunked:
-                raise NotImplementedError("user-defined stopping criteria are not supported in sharded runs")
-            st, table_rows, n_evals, live = self._run_sharded(dist, loglike, table, n, k, seed, scfg, n_deaths,
-                                                              verbose)
+            st, table_rows, n_evals, live = self._run_sharded(dist, loglike, table, n, k, seed, scfg,
+                                                              capacity if chunked else n_deaths, verbose, chunked)
             return self._publish(st, table_rows, n_evals, live, n)
         if verbose:
             print("Generating the initial set of live points with population size {}...".format(n))

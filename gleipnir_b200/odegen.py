@@ -619,7 +619,7 @@ class OdeProtocolLogLikelihood(OdeNetworkLogLikelihood):
     cycles       None, or dict(loc, scale, factors): thermodynamic-cycle products scored by norm(loc, scale) (:72-103)
     """
 
-    def __init__(self, network, sampled, tspan, conditions, rows, preeq=None, cycles=None, log10=True, rtol=1e-8,
+    def __init__(self, network, sampled, tspan, conditions, rows, preeq=None, cycles=None, log10=True, rtol=1e-7,
                  atol=1e-12, max_steps=100000):
         DeviceLogLikelihood.__init__(self)
         self.network = network

@@ -252,7 +252,7 @@ class CoopPlan(object):
             out.append("        }")
         for c, cols in self.lu_ops:
             out.append("        {   // pivot %d" % c)
-            out.append("            const double piv = __shfl_sync(gmask, M[%d], gbase + %d);" % (c, c))
+            out.append("            const double piv = gl::shfl_f64(gmask, M[%d], gbase + %d);" % (c, c))
             out.append("            ok = ok & (fabs(piv) > 1e-300);")
             out.append("            const double ip = 1.0 / piv;")
             out.append("            inv_d = lane == %d ? ip : inv_d;" % c)
@@ -260,40 +260,42 @@ class CoopPlan(object):
                 out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
                 out.append("            M[%d] = lane > %d ? lz : M[%d];" % (c, c, c))
                 for q in cols:
-                    out.append("            M[%d] = fma(-lz, __shfl_sync(gmask, M[%d], gbase + %d), M[%d]);" % (q, q, c, q))
+                    out.append("            M[%d] = fma(-lz, gl::shfl_f64(gmask, M[%d], gbase + %d), M[%d]);" % (q, q, c, q))
             out.append("        }")
         out.append("        return ok;")
         return "\n".join(out)
 
     def cuda_solve(self):
-        """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX)."""
+        """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX).  Updates are
+        single predicated FMAs (pfma_gt / pfma_lt in ode_coop.cuh): the compiler otherwise turns a run of
+        `if (lane > c)` into a branch ladder."""
         nc, nx = self.nc, self.nx
         out = []
         for l in range(nx):
-            out.append("        { const double t = __shfl_sync(gmask, b2, gbase + %d); b = fma(-A[%d], t, b); }" % (l, l))
+            out.append("        { const double t = gl::shfl_f64(gmask, b2, gbase + %d); b = fma(-A[%d], t, b); }" % (l, l))
         for level in self.fwd_levels:
             out.append("        {")
             for c in level:
-                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (c, c))
+                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (c, c))
             for c in level:
-                out.append("            if (lane > %d) b = fma(-M[%d], t%d, b);" % (c, c, c))
+                out.append("            b = gl::pfma_gt(lane, %d, M[%d], t%d, b);" % (c, c, c))
             out.append("        }")
         for scale, bcast in self.bwd_levels:
             mask = 0
             for c in scale:
                 mask |= 1 << c
             out.append("        {")
-            out.append("            if ((0x%xu >> lane) & 1u) b *= inv_d;" % mask)
+            out.append("            b = gl::pmul_mask(lane, 0x%xu, b, inv_d);" % mask)
             for c in bcast:
-                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (c, c))
+                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (c, c))
             for c in bcast:
-                out.append("            if (lane < %d) b = fma(-M[%d], t%d, b);" % (c, c, c))
+                out.append("            b = gl::pfma_lt(lane, %d, M[%d], t%d, b);" % (c, c, c))
             out.append("        }")
         if nx:
             used = sorted({q for l in range(nx) for q in self.leaf_rows[l]})
             out.append("        {")
             for q in used:
-                out.append("            const double t%d = __shfl_sync(gmask, b, gbase + %d);" % (q, q))
+                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (q, q))
             for l in range(nx):
                 e = nc + l
                 out.append("            if (lane == %d) {" % l)

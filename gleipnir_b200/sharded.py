@@ -271,7 +271,44 @@ def run_sharded_native(engine, nccl_comm, n_deaths, batch_k, candidate_sigmas=DE
         _lib.check(engine.lib.gl_ns_finalize_sharded(engine._h, nccl_comm.h, st))
 
     once(candidate_sigmas)
-    if check_overflow and candidate_sigmas > 0.0 and engine.overflowed():
+    if not check_overflow:
+        return False
+    # the verdict of a truncated exchange is identical on every rank, a watchdog timeout is rank-local: take the
+    # maximum over the ranks so that all of them repeat the run, or all of them raise
+    flag = int(engine.state().shard_overflow)
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.tensor([flag], dtype=torch.int32, device=engine.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            flag = int(t.item())
+    except ImportError:          # pragma: no cover
+        pass
+    if flag == 2:
+        raise RuntimeError("sharded run: a peer did not deliver its candidates within GLEIPNIR_PEER_TIMEOUT_S "
+                           "(peer-memory exchange)")
+    if flag and candidate_sigmas > 0.0:
         once(0.0)
         return True
     return False
+
+
+def run_sharded_sliced(engine, nccl_comm, batch_k, max_deaths, should_stop):
+    """Sharded run driven batch by batch from the host (gl_ns_step_sharded): after every batch ``should_stop(state)``
+    is evaluated -- the run state is redundantly identical on every rank, so every rank takes the same decision with
+    no extra collective.  Full candidate exchange (a truncated one could only be validated after the run)."""
+    from . import _lib
+    st = engine._stream()
+    nccl_comm.enable_p2p(batch_k)
+    engine.init()
+    done = 0
+    while done + batch_k <= max_deaths:
+        _lib.check(engine.lib.gl_ns_step_sharded(engine._h, nccl_comm.h, 1, int(batch_k), int(done), 0.0, st))
+        done += batch_k
+        if should_stop(engine.state()):
+            break
+    _lib.check(engine.lib.gl_ns_finalize_sharded(engine._h, nccl_comm.h, st))
+    if int(engine.state().shard_overflow) == 2:
+        raise RuntimeError("sharded run: a peer did not deliver its candidates within GLEIPNIR_PEER_TIMEOUT_S")
+    return done

@@ -296,6 +296,12 @@ GL_API int gl_comm_p2p_disable(gl_comm *c);   /* collective decision of the host
  * the run); 0 exchanges all k candidates per rank. */
 GL_API int gl_ns_advance_sharded(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k,
                                  int64_t n_dead_so_far, double candidate_sigmas, void *stream);
+/* The same loop for a run that is driven batch by batch (monitoring, user-defined stopping criteria evaluated
+ * between batches -- `criterion(nested_sampler) -> bool`, nested_sampling.py:141,215-217): `n_batches` steps, each
+ * one refilling the waiting batch and killing the next; the last batch of the call stays waiting and IS refilled
+ * by the next call (gl_ns_advance_sharded treats the batch that reaches n_deaths_total as the run's last). */
+GL_API int gl_ns_step_sharded(gl_ns *ns, gl_comm *c, int32_t n_batches, int32_t batch_k, int64_t n_dead_so_far,
+                              double candidate_sigmas, void *stream);
 GL_API int gl_ns_finalize_sharded(gl_ns *ns, gl_comm *c, void *stream);
 
 /* Populations whose ordering keys fit in shared memory (N <= 24576) use a single-CTA fused

@@ -2,7 +2,8 @@
 
 Run in the build container only (needs /root/reference, which does not travel):
     python oracle/gen_golden.py
-Writes tests/golden/ref_runs.npz, ref_replay.npz, ref_priors.npz.  The committed
+Writes tests/golden/ref_runs.npz, ref_replay.npz, ref_priors.npz (and, with `stats` as argument,
+ref_stats.npz: ~10 CPU-minutes on 8 cores).  The committed
 .npz files are what tests read; this script is committed so they can be regenerated.
 
 Recorded:
@@ -13,6 +14,9 @@ Recorded:
                stream of replacement (point, logL) fed through a stub sampler, and the
                reference's dead table / Z / H / information -- with ties, -inf and NaN.
   ref_priors   scipy.stats pdf/logpdf/ppf tables + SampledParameter known answers.
+  ref_stats    10-seed ln Z of the unmodified reference on config C1 (d = 2 and 5 Gaussians, N = 500,
+               NumberOfIterations(5000), sampler(10, tc=1): SURVEY 8d) with its reported errors -- the
+               statistical-parity fixture north_star asks for ("within its reported +-sigma over 10 seeds").
 """
 import os
 import sys
@@ -200,8 +204,43 @@ def ode_fixtures():
     print("ode fixtures", {k: v.shape for k, v in out.items()})
 
 
+def _stat_one(args):
+    d, seed = args
+    m = ref_shim.load_reference()
+    SP = m["sampled_parameter"].SampledParameter
+    Sampler = m["samplers"].MetropolisComponentWiseHardNSRejection
+    NOI = m["stopping_criterion"].NumberOfIterations
+    NS = m["nested_sampling"].NestedSampling
+    np.random.seed(seed)
+    sps = [SP(name=i, prior=uniform(loc=-5.0, scale=10.0)) for i in range(d)]
+    ns = NS(sps, _gauss(d), 500, sampler=Sampler(iterations=10, tuning_cycles=1), stopping_criterion=NOI(5000))
+    logz, err = ref_shim.run_reference(ns, m["nested_sampling"])
+    return d, seed, float(logz), float(err), float(ns.information)
+
+
+def stat_cases():
+    import multiprocessing as mp
+    jobs = [(d, seed) for d in (2, 5) for seed in range(10)]
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        res = pool.map(_stat_one, jobs, chunksize=1)
+    out = {}
+    for d in (2, 5):
+        rows = sorted(r for r in res if r[0] == d)
+        out["gauss%d/seeds" % d] = np.array([r[1] for r in rows])
+        out["gauss%d/logZ" % d] = np.array([r[2] for r in rows])
+        out["gauss%d/logZ_err" % d] = np.array([r[3] for r in rows])
+        out["gauss%d/information" % d] = np.array([r[4] for r in rows])
+        print("C1 d=%d: ln Z = %.4f +- %.4f (seed scatter), reported sigma %.4f, truth %.4f"
+              % (d, out["gauss%d/logZ" % d].mean(), out["gauss%d/logZ" % d].std(ddof=1),
+                 out["gauss%d/logZ_err" % d].mean(), -d * np.log(10.0)))
+    np.savez_compressed(os.path.join(OUT, "ref_stats.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "stats" in sys.argv[1:]:
+        stat_cases()
+        sys.exit(0)
     mods = ref_shim.load_reference()
     full_runs(mods)
     replay_cases(mods)

@@ -48,6 +48,22 @@ def main():
     logz, err = ns.run()
     res["api_logz"] = np.array([logz, err, float(ns._n_evals)])
     res["api_table"] = ns.dead_points.to_numpy()
+
+    # a user-defined stopping criterion (no closed-form death count): the sharded run is driven batch by batch
+    class StopAfter(object):
+        def __init__(self, nmax):
+            self.nmax = nmax
+
+        def __call__(self, sampler):
+            return sampler._n_iterations >= self.nmax
+    whole = 2400                                             # a multiple of k: sliced runs stop on batch boundaries
+    ns_a = NestedSampling(sps, like, n, sampler=MetropolisComponentWiseHardNSRejection(iterations=4, tuning_cycles=1),
+                          stopping_criterion=NumberOfIterations(whole), batch_k=k, seed=seed)
+    ns_b = NestedSampling(sps, like, n, sampler=MetropolisComponentWiseHardNSRejection(iterations=4, tuning_cycles=1),
+                          stopping_criterion=StopAfter(whole), batch_k=k, seed=seed)
+    ra, rb = ns_a.run(), ns_b.run()
+    res["sliced_equal"] = np.array([float(ra == rb), float(np.array_equal(ns_a.dead_points.to_numpy(),
+                                                                          ns_b.dead_points.to_numpy()))])
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
     dist.barrier()
     dist.destroy_process_group()

@@ -72,3 +72,6 @@ def test_native_sharded_run_on_two_gpus_matches_oracle_shards(cuda, tmp_path):
         np.testing.assert_allclose(got[rk]["api_logz"][0], ora[0].result["logZ"], rtol=1e-12)
         assert got[rk]["api_logz"][2] == sum(o.result["n_evals"] for o in ora)
     assert abs(want_table[:, 1].sum() - 1.0) < 1e-12
+    # user-defined stopping criterion in a sharded run == the closed-form run (same batches, same table)
+    for rk in range(world):
+        assert np.array_equal(got[rk]["sliced_equal"], [1.0, 1.0])
