@@ -313,6 +313,28 @@ def c5_flops_per_step(net):
     return dense, sparse
 
 
+def finite_population(env, like, table, n, seed):
+    """n prior draws CONDITIONED on a finite likelihood, as device tensors: the live set of a C5 run at the moment
+    its first phase ends.  ~59 % of the prior box has likelihood -inf (the half-normal term of
+    run_jarm_multinest.py:39-40 has no density below the measured value), so a run's first 0.59*N/k batches only
+    clear those points under a wall of -inf; every batch after that -- thousands -- runs under a finite wall, and
+    that is the state the timed steps start from."""
+    torch = env.torch
+    lo = torch.tensor([a for _, a, b in table], dtype=torch.float64, device="cuda")
+    sc = torch.tensor([b for _, a, b in table], dtype=torch.float64, device="cuda")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    xs, ls, have = [], [], 0
+    while have < n:
+        x = lo + sc * torch.rand((max(4096, n), len(table)), generator=g, dtype=torch.float64, device="cuda")
+        l = like.evaluate(x)
+        m = torch.isfinite(l)
+        xs.append(x[m])
+        ls.append(l[m])
+        have += int(m.sum())
+    return torch.cat(xs)[:n].contiguous(), torch.cat(ls)[:n].contiguous()
+
+
 def run_c5(args, env):
     """Headline: K timed NS batches of the running C5 run.  Returns the pieces of the JSON line."""
     torch, L, world, rank = env.torch, env.L, env.world, env.rank
@@ -344,7 +366,8 @@ def run_c5(args, env):
                 eng.refill()
             eng.kill(k)
     t0 = time.perf_counter()
-    eng.init()                                              # N prior draws + N likelihood evaluations (setup, untimed)
+    x0, l0 = finite_population(env, like, table, eng.N, 11 + rank)      # setup, untimed
+    eng.init(x0, l0)
     advance(k, 0)                                           # first kill: from here on a step = refill + kill
     torch.cuda.synchronize()
     t_init = time.perf_counter() - t0
@@ -390,8 +413,10 @@ def run_c5(args, env):
 
 
 def run_c5_e2e(args, env, k):
-    """The public call, bounded: NestedSampling(...).run() with NumberOfIterations(2k) at N = 10^5 -- priors and
-    config in from the host, initial population, one refill, finalisation, the dead-point table back on the host."""
+    """The public call, bounded: NestedSampling(..., initial_live_points=host array).run() with NumberOfIterations(2k)
+    at N = 10^5 -- priors, config and the 14.4 MB live set in from the host, its 10^5 likelihood evaluations, one
+    refilled batch, finalisation, the dead-point table back on the host.  The live set is the finite-likelihood
+    population of finite_population() (drawn outside the timed region)."""
     torch, world = env.torch, env.world
     from gleipnir_b200 import jarm
     from gleipnir_b200.nestedsampling import NestedSampling
@@ -401,11 +426,13 @@ def run_c5_e2e(args, env, k):
     n_runs = max(1, min(args.steps, 2))
     t_tot, ev_tot, rows = 0.0, 0.0, 0
     like = jarm.jarm_loglikelihood()
+    table = [(env.L.GL_PRIOR_UNIFORM, a, b) for a, b in jarm.jarm_prior_table()]
+    x_host = finite_population(env, like, table, w["population"], 77)[0].cpu().numpy()      # same on every rank
     for i in range(n_runs):
         sps = jarm.jarm_sampled_parameters()
         ns = NestedSampling(sps, like, w["population"], sampler=MetropolisComponentWiseHardNSRejection(
             iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"]),
-            stopping_criterion=NumberOfIterations(2 * k), batch_k=k, seed=700 + i)
+            stopping_criterion=NumberOfIterations(2 * k), batch_k=k, seed=700 + i, initial_live_points=x_host)
         env.barrier()
         like.counters(reset=True)
         t0 = time.perf_counter()
@@ -417,12 +444,13 @@ def run_c5_e2e(args, env, k):
     t_max = env.reduce([t_tot], "MAX")[0]
     ev = env.reduce([ev_tot], "SUM")[0]
     d = w["d"]
-    return dict(value=ev / t_max, unit="evals/s", h2d_bytes_per_step=int(24 * d + ctypes.sizeof(env.L.gl_ns_config)),
+    return dict(value=ev / t_max, unit="evals/s",
+                h2d_bytes_per_step=int(24 * d + ctypes.sizeof(env.L.gl_ns_config) + w["population"] * d * 8),
                 d2h_bytes_per_step=int(rows * 8 * (d + 2) + w["population"] * d * 8 + 2 * ctypes.sizeof(env.L.gl_ns_state)),
                 ms_per_step=1e3 * t_max / n_runs, runs=n_runs,
                 call="NestedSampling(jarm priors, jarm likelihood, 1e5, sampler(10, burn 10, tc 1), NumberOfIterations(2k), "
-                     "batch_k=k).run(): initial population (1e5 evaluations) + one refilled batch + final term + "
-                     "dead_points on the host")
+                     "batch_k=k, initial_live_points=<host array, finite-likelihood prior draws>).run(): live set host->device, "
+                     "its 1e5 evaluations, one refilled batch, final term, dead_points on the host")
 
 
 def run_c2(args, env, reps):
@@ -600,7 +628,9 @@ def run_b200_arm(args):
                             ode="RODAS4, rtol %g atol %g" % (like.rtol, like.atol),
                             evals_counted="integrated on the device (kernel counter); the reference's own count, which "
                                           "includes trial moves rejected by the prior alone, is nominal_evals",
-                            nominal_evals=c5["nominal_evals"], init_s=c5["t_init"],
+                            nominal_evals=c5["nominal_evals"], setup_s=c5["t_init"],
+                            start_state="live set = prior draws conditioned on a finite likelihood (the state of a run when its "
+                                        "-inf phase ends: 59 % of the prior box lies outside the half-normal term's support)",
                             l2="flushed between timed steps (256 MB memset)",
                             parallelism=("live set sharded over %d ranks (N/world each); per step one fused kernel exchanges the "
                                          "candidate logL over NVLink peer memory; k = 800 walkers per GPU (weak in k)" % world)

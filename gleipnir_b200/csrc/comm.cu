@@ -218,8 +218,8 @@ int gl_comm_all_gather_f64(gl_comm *c, const double *send_dev, double *recv_dev,
 // all-gather -> commit -> refill, all on `stream`.
 }  // extern "C"
 
-// `open_ended`: every batch of this call will be refilled by a later call (stepping a long run batch by batch);
-// otherwise the batch that reaches n_deaths_total is the run's last and is left for the final term.
+// `open_ended`: the call's last batch may be refilled by a later call (stepping a long run batch by batch);
+// the device-side protocol is the same, the flag only documents the caller's intent.
 static int advance_sharded_impl(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, int32_t batch_k, int64_t n_dead_so_far,
                                 double candidate_sigmas, bool open_ended, void *stream);
 
@@ -262,7 +262,9 @@ static int advance_sharded_impl(gl_ns *ns, gl_comm *c, int64_t n_deaths_total, i
         }
         first = false;
         const int32_t m = gl_ns_shard_candidate_count(k, c->world, n_local, candidate_sigmas);
-        gl_ns_internal_commit_refills(ns, (open_ended || done + k < n_deaths_total) ? 1 : 0);
+        // "a refill follows inside this call": only then may the commit leave its bookkeeping to the walkers.  The
+        // last batch of an open-ended call is refilled by a LATER call, or finalised instead: it records its own rows.
+        gl_ns_internal_commit_refills(ns, done + k < n_deaths_total ? 1 : 0);
         if (c->p2p_ready && m <= c->tables.cap && n_local <= 196608 && (int64_t)c->world * m <= 196608) {
             // fused step: candidates, exchange over NVLink peer memory and commit in ONE launch
             c->epoch += 1;

@@ -90,14 +90,26 @@ class DeviceEngine(object):
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
 
+    def adopt_population(self, live, logl):
+        """Start the run from a caller-supplied population (resuming a run, or a population conditioned by the
+        caller) instead of prior draws: every later ``init()`` -- also the ones the sharded drivers issue -- copies
+        these rows.  ``live`` [N, d] and ``logl`` [N]: numpy arrays or tensors (any device)."""
+        self._adopted = (live, logl)
+
     @_on_device
     def init(self, live=None, logl=None):
         """Draw + evaluate the initial population (or adopt a caller-supplied one)."""
         torch = _torch()
         skip = 0
+        if live is None and getattr(self, "_adopted", None) is not None:
+            live, logl = self._adopted
         if live is not None:
-            self.live.copy_(torch.as_tensor(np.asarray(live, dtype=np.float64)).to(self.device))
-            self.logl.copy_(torch.as_tensor(np.asarray(logl, dtype=np.float64)).to(self.device))
+            def dev(a):
+                if not isinstance(a, torch.Tensor):
+                    a = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+                return a.to(device=self.device, dtype=torch.float64)
+            self.live.copy_(dev(live).reshape(self.N, self.d))
+            self.logl.copy_(dev(logl).reshape(self.N))
             skip = 1
         _lib.check(self.lib.gl_ns_init(self._h, skip, self._stream()))
 

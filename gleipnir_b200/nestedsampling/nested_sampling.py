@@ -42,7 +42,8 @@ def _default_sampler():
 class NestedSampling(NestedSamplingBase):
 
     def __init__(self, sampled_parameters, loglikelihood, population_size, sampler=None,
-                 stopping_criterion=None, batch_k=None, seed=None, device=None, sharded=None):
+                 stopping_criterion=None, batch_k=None, seed=None, device=None, sharded=None,
+                 initial_live_points=None):
         self.sampled_parameters = sampled_parameters
         self._sampled_parameters_dict = {sp.name: sp for sp in sampled_parameters}
         self.loglikelihood = loglikelihood
@@ -55,6 +56,9 @@ class NestedSampling(NestedSamplingBase):
         self.seed = seed
         self.device = device
         self.sharded = sharded
+        # extension: start from these live points [population_size, d] (host array) instead of prior draws --
+        # resuming a run, or a population the caller has conditioned; their log-likelihoods are evaluated on the device
+        self.initial_live_points = initial_live_points
 
         self._alpha = population_size / (population_size + 1)
         self._evidence = 0.0
@@ -143,6 +147,7 @@ class NestedSampling(NestedSamplingBase):
         eng = DeviceEngine(table, loglike, n_loc, k, n_deaths, seed=int(seed_t.item()),
                            device=self.device, row_offset=off, global_population=n, **scfg)
         self._engine = eng
+        self._adopt_initial(eng, loglike, off, n_loc)
         if chunked:
             def should_stop(state):
                 self._n_iterations = int(state.n_dead)
@@ -193,6 +198,7 @@ class NestedSampling(NestedSamplingBase):
             print("Generating the initial set of live points with population size {}...".format(n))
         eng = DeviceEngine(table, loglike, n, k, capacity, seed=seed, device=self.device, **scfg)
         self._engine = eng
+        self._adopt_initial(eng, loglike, 0, n)
         if verbose:
             print("Evaluating the loglikelihood function for each live point...")
         eng.init()
@@ -226,6 +232,17 @@ class NestedSampling(NestedSamplingBase):
         else:
             table_rows, _idx, _step = eng.dead_table()
         return self._publish(st, table_rows, int(st.n_evals), eng.live.cpu().numpy(), n)
+
+    def _adopt_initial(self, eng, loglike, offset, count):
+        if self.initial_live_points is None:
+            return
+        import torch
+        x = np.asarray(self.initial_live_points, dtype=np.float64)
+        if x.shape != (int(self.population_size), eng.d):
+            raise ValueError("initial_live_points must be [population_size, number of sampled parameters]")
+        with torch.cuda.device(eng.device):
+            xt = torch.as_tensor(np.ascontiguousarray(x[offset:offset + count])).to(eng.device)   # host -> device
+            eng.adopt_population(xt, loglike.evaluate(xt))
 
     def _publish(self, st, table_rows, n_evals, live, n):
         self._state = st
