@@ -7,6 +7,8 @@
 //            -> walkers (tuning_cycles + 1 launches, walker.cu) -> end_walk
 #include <new>
 #include <vector>
+#include <string>
+#include <thread>
 #include <stdlib.h>
 #include "engine.cuh"
 #include "philox.cuh"
@@ -2249,6 +2251,34 @@ int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream) {
     ns->defer_ok = false;
     if (rc == GL_OK) rc = gl::flush_end_walk(ns, st);
     return rc;
+}
+
+// R independent runs (the seeds of one problem, the models of a selection sweep) advanced concurrently: one host
+// thread per engine enqueues that engine's whole run on its own stream, so the launches of the runs interleave and
+// their kernels overlap on the device -- a single small run offers a few tens of thousands of threads to a machine
+// with 3*10^5 of them (HypSelector.run_nested_sampling runs its models one after another, hyp_selector.py:236-248).
+int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams) {
+    GL_REQUIRE(engines != nullptr && streams != nullptr && n_deaths_total != nullptr && n >= 1, "bad argument");
+    for (int i = 0; i < n; ++i) GL_REQUIRE(engines[i] != nullptr, "engine %d is NULL", i);
+    int dev = 0;
+    GL_CUDA(cudaGetDevice(&dev));
+    std::vector<int> rcs((size_t)n, GL_OK);
+    std::vector<std::string> msgs((size_t)n);
+    std::vector<std::thread> threads;
+    threads.reserve((size_t)n);
+    for (int i = 0; i < n; ++i)
+        threads.emplace_back([&, i]() {
+            cudaSetDevice(dev);
+            rcs[(size_t)i] = gl_ns_advance(engines[i], n_deaths_total[i], streams[i]);
+            if (rcs[(size_t)i] != GL_OK) msgs[(size_t)i] = gl::error_buffer();
+        });
+    for (auto &t : threads) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rcs[(size_t)i] != GL_OK) {
+            gl::set_error("engine %d: %s", i, msgs[(size_t)i].c_str());
+            return rcs[(size_t)i];
+        }
+    return GL_OK;
 }
 
 int gl_ns_finalize(gl_ns *ns, void *stream) {

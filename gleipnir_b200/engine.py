@@ -36,7 +36,7 @@ class DeviceEngine(object):
 
     def __init__(self, prior_table, model_handle, population_size, batch_k, n_deaths_capacity, iterations=100,
                  burn_in=0, tuning_cycles=0, proposal=0, seed=0, device=None, walker_lanes=0, row_offset=0,
-                 global_population=None):
+                 global_population=None, stream=None):
         torch = _torch()
         self.lib = _lib.load()
         if hasattr(model_handle, "device_model"):       # a DeviceLogLikelihood: keep it alive with the engine
@@ -44,6 +44,7 @@ class DeviceEngine(object):
             model_handle = model_handle.device_model()
         self.d = len(prior_table)
         self.N = int(population_size)
+        self.stream = stream                             # torch.cuda.Stream of this engine (None: the current stream)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -88,7 +89,12 @@ class DeviceEngine(object):
             self._h = ctypes.c_void_p()
 
     def _stream(self):
+        if self.stream is not None:
+            return self.stream.cuda_stream
         return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def _torch_stream(self):
+        return self.stream if self.stream is not None else _torch().cuda.current_stream(self.device)
 
     def adopt_population(self, live, logl):
         """Start the run from a caller-supplied population (resuming a run, or a population conditioned by the
@@ -217,13 +223,15 @@ class DeviceEngine(object):
         torch = _torch()
         st = self.state()
         rows = int(st.n_rows)
-        table = torch.empty((rows, self.d + 2), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.gl_ns_export_dead(self._h, table.data_ptr(), self._stream()))
-        # pinned staging (torch's caching host allocator recycles the block between runs): the copy
-        # runs at PCIe rate instead of through a pageable bounce buffer
-        host = torch.empty((rows, self.d + 2), dtype=torch.float64, pin_memory=True)
-        host.copy_(table, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        ts = self._torch_stream()
+        with torch.cuda.stream(ts):
+            table = torch.empty((rows, self.d + 2), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.gl_ns_export_dead(self._h, table.data_ptr(), self._stream()))
+            # pinned staging (torch's caching host allocator recycles the block between runs): the copy
+            # runs at PCIe rate instead of through a pageable bounce buffer
+            host = torch.empty((rows, self.d + 2), dtype=torch.float64, pin_memory=True)
+            host.copy_(table, non_blocking=True)
+            ts.synchronize()
         return host.numpy()
 
     @_on_device

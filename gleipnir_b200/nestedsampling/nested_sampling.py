@@ -170,8 +170,22 @@ class NestedSampling(NestedSamplingBase):
         dist.all_gather_into_tensor(live, eng.live)
         return st, table_rows, int(evals.item()), live.cpu().numpy()
 
-    def run(self, verbose=False):
-        loglike = require_device_loglikelihood(self.loglikelihood)
+    def run_replicas(self, seeds, max_concurrent=16):
+        """This run repeated once per seed, all of them concurrently on the device (gleipnir_b200/replicas.py);
+        returns the finished ``NestedSampling`` objects, one per seed -- e.g. the 10-seed scatter of ln Z that the
+        reported ``log_evidence_error`` should be compared with."""
+        import copy
+        from ..replicas import run_many
+        clones = [NestedSampling(self.sampled_parameters, self.loglikelihood, self.population_size,
+                                 sampler=copy.copy(self.sampler), stopping_criterion=self.stopping_criterion,
+                                 batch_k=self.batch_k, seed=int(s), device=self.device, sharded=False,
+                                 initial_live_points=self.initial_live_points) for s in seeds]
+        run_many(clones, max_concurrent=max_concurrent)
+        return clones
+
+    def _prepare(self, loglike):
+        """Everything run() settles before touching the device: (loglike, prior table, N, k, seed, sampler config,
+        closed-form death count or None, chunked, dead-log capacity)."""
         if loglike.ndim != len(self.sampled_parameters):
             raise ValueError("loglikelihood.ndim = %d but %d sampled parameters"
                              % (loglike.ndim, len(self.sampled_parameters)))
@@ -189,6 +203,11 @@ class NestedSampling(NestedSamplingBase):
             capacity = int(getattr(self.stopping_criterion, "max_iterations", 100 * n))
         else:
             capacity = n_deaths
+        return loglike, table, n, k, seed, scfg, n_deaths, chunked, capacity
+
+    def run(self, verbose=False):
+        loglike = require_device_loglikelihood(self.loglikelihood)
+        loglike, table, n, k, seed, scfg, n_deaths, chunked, capacity = self._prepare(loglike)
         dist = self._dist_world()
         if dist is not None:
             st, table_rows, n_evals, live = self._run_sharded(dist, loglike, table, n, k, seed, scfg,

@@ -212,6 +212,11 @@ GL_API int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_
 
 /* nested_sampling.py:183-203: final live-point term; appends the survivors to the
  * dead buffers in index order with weight X/(#survivors). */
+/* `n` independent engines (seeds of one problem, models of a selection sweep -- HypSelector.run_nested_sampling,
+ * pysb_utilities/hyp_selector.py:236-248, runs them one after another) advanced to n_deaths_total[i] deaths each,
+ * concurrently: one host thread per engine enqueues on streams[i], so the runs' kernels overlap on the device.
+ * Per-engine results are identical to n separate gl_ns_advance calls. */
+GL_API int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams);
 GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 
 /* `dead_points` (nested_sampling.py:211,338-344) assembled on the device: table_dev[n_rows, d+2]
