@@ -130,7 +130,8 @@ struct CoopCounters {
 template <class Net>
 struct CoopOde {
     static constexpr int NS = Net::NS, NC = Net::NC, NX = Net::NX, NXA = Net::NXA, GL = Net::GL, NR = Net::NR;
-    static constexpr int LD = Net::LD, NRM = Net::NRM, NRP = Net::NRP;
+    static constexpr int LD = Net::LD, NRM = Net::NRM, NRP = Net::NRP, XS = Net::XS;
+    static constexpr int SD = (4 * NRP + 2 > 2 * XS ? 4 * NRP + 2 : 2 * XS);
 
     struct alignas(16) Tables {         // per block, in shared memory: the network's index lists
         unsigned int rtab[NRP];
@@ -142,7 +143,8 @@ struct CoopOde {
     struct alignas(16) Shared {         // per group, in shared memory
         double J[NS * LD];              // Jacobian rows; entries outside the structural pattern stay 0
         double sv[2 * NRP + 2];         // v_r, -v_r; [2*NRP] = 0
-        double sd[4 * NRP + 2];         // dv_r/dy_a, -, dv_r/dy_b, -; [4*NRP] = 0
+        double sd[SD];                  // dv_r/dy_a, -, dv_r/dy_b, -; [4*NRP] = 0.  Dead once the Jacobian rows are
+                                        // assembled: the substitutions use it as their two broadcast buffers
         double c[NRP];                  // sf_r * p[k_r] of the running solve (0 for the padding reactions)
         double k[6 * NS];               // stage vectors of the running step
         double dump[2];                 // store target of the lanes that own no Jacobian row
@@ -198,14 +200,10 @@ struct CoopOde {
 
     // f of this lane's core / leaf species at the state the rates were evaluated at
     static __device__ __forceinline__ void rhs_rows(const Shared &sh, const Tables &T, int lane, double &f, double &f2) {
-        double fa = 0.0, fb = 0.0;
+        double fa[4] = {0.0, 0.0, 0.0, 0.0};               // four short dependent chains instead of one long one
 #pragma unroll
-        for (int e = 0; e < Net::EF; ++e) {
-            const double t = sh.sv[T.ftab[e * GL + lane]];
-            if (e & 1) fb += t;
-            else fa += t;
-        }
-        f = fa + fb;
+        for (int e = 0; e < Net::EF; ++e) fa[e & 3] += sh.sv[T.ftab[e * GL + lane]];
+        f = (fa[0] + fa[1]) + (fa[2] + fa[3]);
         f2 = 0.0;
         if (NX > 0 && lane < NX) {
 #pragma unroll
@@ -250,6 +248,7 @@ struct CoopOde {
         const double ih = 1.0 / h, diag = 1.0 / (ROD_GAMMA * h);
         // ---- Jacobian rows into shared memory, then the core row of M into registers ----------
         publish(sh, lane, gmask, yi, y2);
+        if (lane == 0) sh.sd[4 * NRP] = sh.sd[4 * NRP + 1] = 0.0;     // (the previous step's substitutions used sd)
         rates<true>(sh, T, lane, gmask);
         jac_rows(sh, T, lane);
         double F, F2;
@@ -283,6 +282,9 @@ struct CoopOde {
         double inv_d = 1.0, inv_d2 = 0.0;
         const bool ok = Net::lu(M, A, sh.J, diag, lane, GL == 32 ? 0xffffffffu : gmask, gbase, inv_d, inv_d2);
         if (!__all_sync(gmask, ok)) return false;
+        const unsigned gtm = (1u << lane) - 1u;          // bit c set: lane > c
+        const unsigned ltm = ~((2u << lane) - 1u);       // bit c set: lane < c
+        Net::scale_u(M, inv_d, ltm);
         // ---- stages: k_s = M^-1 (f(y + sum_j a_sj k_j) + (1/h) sum_j c_sj k_j) ------------------
         const bool core = lane < NC, leaf = NX > 0 && lane < NX;
         double *kc = sh.k + (core ? lane : 0), *kl = sh.k + NC + (leaf ? lane : 0);
@@ -308,7 +310,7 @@ struct CoopOde {
             }
             b = fma(ih, r, F);
             b2 = fma(ih, r2, F2);
-            Net::solve(M, A, sh.J, inv_d, inv_d2, b, b2, lane, GL == 32 ? 0xffffffffu : gmask, gbase);
+            Net::solve(M, A, sh.J, inv_d, inv_d2, b, b2, lane, GL == 32 ? 0xffffffffu : gmask, gtm, ltm, sh.sd);
             if (core) kc[stage * NS] = b;
             if (leaf) kl[stage * NS] = b2;
         }

@@ -333,8 +333,8 @@ class MassActionNetwork(object):
                   "    static constexpr int NS = %d, NC = %d, NX = %d, NXA = %d, NP = %d, NR = %d, NOBS = %d, GL = %d, "
                   "LD = %d;" % (ns, pl.nc, pl.nx, T["nxa"], self.np_, len(self.reactions), len(self.obs_names), pl.gl,
                                 T["ld"]),
-                  "    static constexpr int NRM = %d, NRP = %d, EF = %d, EF2 = %d, EJ = %d, EJ2 = %d;"
-                  % (T["nrm"], T["nrp"], T["ef"], T["ef2"], T["ej"], T["ej2"])]
+                  "    static constexpr int NRM = %d, NRP = %d, EF = %d, EF2 = %d, EJ = %d, EJ2 = %d, XS = %d;"
+                  % (T["nrm"], T["nrp"], T["ef"], T["ef2"], T["ej"], T["ej2"], pl.xs_stride())]
         struct += acc
         struct += ["    // M = diag*I - J factored in place: lane i holds core row i (L below the diagonal, U on and",
                    "    // above it), A the lane's multipliers of the leaf columns; J = Jacobian rows in shared memory",
@@ -342,10 +342,13 @@ class MassActionNetwork(object):
                    "double diag, int lane,",
                    "                                              unsigned gmask, int gbase, double &inv_d, double &inv_d2) {",
                    pl.cuda_lu(), "    }",
+                   "    // U -> D^-1 U; ltm = bit mask of the lanes above this one",
+                   "    static __device__ __forceinline__ void scale_u(double (&M)[NC], double inv_d, unsigned ltm) {",
+                   pl.cuda_scale_u(), "    }",
                    "    static __device__ __forceinline__ void solve(const double (&M)[NC], const double (&A)[NXA], "
                    "const double *J, double inv_d,",
                    "                                                 double inv_d2, double &b, double &b2, int lane, "
-                   "unsigned gmask, int gbase) {",
+                   "unsigned gmask, unsigned gtm, unsigned ltm, double *xs) {",
                    pl.cuda_solve(), "    }", "};"]
         return "\n".join(tables + struct)
 

@@ -202,6 +202,8 @@ class CoopPlan(object):
                 pq = M[c, q]
                 M[below, q] = M[below, q] - lm[below] * pq
         inv_d = np.array([1.0 / M[i, i] if i < nc else 1.0 for i in range(gl)])
+        for i in range(nc):                                     # U -> D^-1 U (cuda_scale_u)
+            M[i, i + 1:] *= inv_d[i]
         # solve
         b = np.zeros(gl)
         b[:nc] = bi[:nc]
@@ -214,9 +216,8 @@ class CoopPlan(object):
             for c in level:
                 m = lane > c
                 b[m] = b[m] - M[m, c] * t[c]
+        b = b * inv_d
         for scale, bcast in self.bwd_levels:
-            for c in scale:
-                b[c] *= inv_d[c]
             t = {c: b[c] for c in bcast}
             for c in bcast:
                 m = lane < c
@@ -265,45 +266,70 @@ class CoopPlan(object):
         out.append("        return ok;")
         return "\n".join(out)
 
+    def xs_stride(self):
+        """Doubles per broadcast buffer of the substitution: one slot per lane plus one per leaf."""
+        return max(self.gl, self.nc) + max(self.nx, 0)
+
+    def cuda_scale_u(self):
+        """After the factorisation: U -> D^-1 U (unit upper triangular), so that the backward substitution needs
+        one unconditional scaling of the right-hand side instead of a predicated one per level."""
+        return "\n".join("        if (ltm & %du) M[%d] *= inv_d;" % (1 << q if q < 32 else 0, q) for q in range(1, self.nc))
+
     def cuda_solve(self):
-        """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX).  Updates are
-        single predicated FMAs (pfma_gt / pfma_lt in ode_coop.cuh): the compiler otherwise turns a run of
-        `if (lane > c)` into a branch ladder."""
+        """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX).
+
+        The vector travels through shared memory: at every level of the schedule all lanes store their entry
+        (two buffers, alternating, so one warp-level sync per level orders stores and loads), the columns of the
+        level are read back as broadcasts (one LDS.64 each, where a 64-bit shuffle costs two SHFL and the moves
+        that re-pair the halves) and applied as predicated FMAs.  Predicates are bit tests of two per-lane
+        masks, gtm = lanes below this one, ltm = lanes above (one LOP3 producing the predicate; chains of
+        `lane > c` comparisons make the compiler build branch ladders).  M holds L below the diagonal and
+        D^-1 U above it."""
         nc, nx = self.nc, self.nx
-        out = []
-        for l in range(nx):
-            out.append("        { const double t = gl::shfl_f64(gmask, b2, gbase + %d); b = fma(-A[%d], t, b); }" % (l, l))
+        leaf0 = max(self.gl, self.nc)
+        out = ["        int buf = 0;"]
+        if nx:
+            out.append("        if (lane < %d) xs[%d + lane] = b2;" % (nx, leaf0))
+            out.append("        __syncwarp(gmask);")
+            for l in range(nx):
+                out.append("        b = fma(-A[%d], xs[%d], b);" % (l, leaf0 + l))
         for level in self.fwd_levels:
             out.append("        {")
+            out.append("            double *X = xs + buf * XS; buf ^= 1;")
+            out.append("            X[lane] = b;")
+            out.append("            __syncwarp(gmask);")
             for c in level:
-                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (c, c))
+                out.append("            const double t%d = X[%d];" % (c, c))
             for c in level:
-                out.append("            b = gl::pfma_gt(lane, %d, M[%d], t%d, b);" % (c, c, c))
+                out.append("            if (gtm & %du) b = fma(-M[%d], t%d, b);" % (1 << c, c, c))
             out.append("        }")
+        out.append("        b *= inv_d;")
         for scale, bcast in self.bwd_levels:
-            mask = 0
-            for c in scale:
-                mask |= 1 << c
+            if not bcast:
+                continue
             out.append("        {")
-            out.append("            b = gl::pmul_mask(lane, 0x%xu, b, inv_d);" % mask)
+            out.append("            double *X = xs + buf * XS; buf ^= 1;")
+            out.append("            X[lane] = b;")
+            out.append("            __syncwarp(gmask);")
             for c in bcast:
-                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (c, c))
+                out.append("            const double t%d = X[%d];" % (c, c))
             for c in bcast:
-                out.append("            b = gl::pfma_lt(lane, %d, M[%d], t%d, b);" % (c, c, c))
+                out.append("            if (ltm & %du) b = fma(-M[%d], t%d, b);" % (1 << c, c, c))
             out.append("        }")
         if nx:
-            used = sorted({q for l in range(nx) for q in self.leaf_rows[l]})
             out.append("        {")
-            for q in used:
-                out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (q, q))
+            out.append("            double *X = xs + buf * XS; buf ^= 1;")
+            out.append("            X[lane] = b;")
+            out.append("            __syncwarp(gmask);")
             for l in range(nx):
                 e = nc + l
                 out.append("            if (lane == %d) {" % l)
                 for q in self.leaf_rows[l]:
-                    out.append("                b2 = fma(J[%d * LD + %d], t%d, b2);" % (e, q, q))
+                    out.append("                b2 = fma(J[%d * LD + %d], X[%d], b2);" % (e, q, q))
                 out.append("                b2 *= inv_d2;")
                 out.append("            }")
             out.append("        }")
+        out.append("        __syncwarp(gmask);")
         return "\n".join(out)
 
     def flops_dense(self, n_reactions):
