@@ -4,11 +4,18 @@
 Same constructor, ``run(verbose=False) -> (log_evidence, log_evidence_error)``, read-only
 properties (``evidence``, ``evidence_error``, ``log_evidence``, ``log_evidence_error``,
 ``information``, ``dead_points``), ``posteriors``, ``max_loglikelihood``, ``deviance_ic``,
-``best_fit_likelihood`` and the inherited ABC helpers.  Extra keyword arguments (all
-optional, defaults keep the reference call verbatim):
+``best_fit_likelihood`` and the inherited ABC helpers.  Extra keyword arguments (all optional;
+the call SHAPE stays the reference's, the default ``batch_k`` does change the sequencing):
 
     batch_k   deaths per device step.  1 reproduces upstream's one-death-per-iteration
-              sequencing exactly; the default ``None`` picks ``max(1, N // 10)``.
+              sequencing exactly; the default ``None`` picks ``max(1, N // 10)``, i.e. batched
+              Nested Sampling: the k worst die together, each with weight X/(N+1), then
+              X <- X (N-k+1)/(N+1)  (measured unbiased for k <= N/2).
+              Stopping criteria count DEATHS (``_n_iterations``), as upstream counts iterations:
+              ``RemainingPriorMass(c)`` stops after the first n with (N/(N+1))**n <= c -- upstream's
+              literal predicate -- while the engine's own ln X after those n deaths differs from
+              ln c by O(k/N) for k > 1.  User-defined criteria are polled once per batch, so a run
+              can pass their threshold by up to k-1 deaths.
     seed      Philox key.  Default: drawn from numpy's global RNG, so ``np.random.seed``
               still makes a script reproducible.
     device    torch device (default: current CUDA device).
@@ -234,7 +241,7 @@ class NestedSampling(NestedSamplingBase):
             else:
                 eng.advance(n_deaths)
         else:
-            done = 0
+            done, stopped = 0, False
             while done < capacity:
                 done = min(capacity, done + k)
                 eng.advance(done)
@@ -243,7 +250,12 @@ class NestedSampling(NestedSamplingBase):
                 self._evidence = float(np.exp(st.log_z))
                 self._information = float(st.information)
                 if self._stopping_criterion():
+                    stopped = True
                     break
+            if not stopped:
+                warnings.warn("the stopping criterion was still False after %d deaths, the capacity of the dead-point "
+                              "log (stopping_criterion.max_iterations, default 100 x population): the run was "
+                              "finalised there and is NOT converged by its own criterion" % capacity)
         eng.finalize()
         st = eng.state()
         if k <= 8192:

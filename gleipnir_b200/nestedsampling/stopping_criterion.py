@@ -23,7 +23,10 @@ class NumberOfIterations(object):
 
 
 class RemainingPriorMass(object):
-    """Stop once ``alpha**n <= cutoff`` (stopping_criterion.py:48-57)."""
+    """Stop once ``alpha**n <= cutoff`` (stopping_criterion.py:48-57), n = deaths so far, alpha = N/(N+1):
+    upstream's literal predicate, evaluated in closed form.  With ``batch_k`` > 1 the engine's own estimate of the
+    remaining prior mass after n deaths (X shrinks by (N-k+1)/(N+1) per batch) differs from alpha**n by O(k/N) in
+    the logarithm; the criterion deliberately keeps upstream's definition in terms of the death count."""
 
     def __init__(self, cutoff):
         self.cutoff = cutoff

@@ -17,7 +17,7 @@ ODE_RTOL = 1e-6
 @pytest.fixture(scope="module")
 def problem(cuda):
     from gleipnir_b200 import jarm, networks
-    like = jarm.jarm_loglikelihood()                       # the bench's object: RODAS4 at rtol 1e-7
+    like = jarm.jarm_loglikelihood()                       # the bench's object: RODAS4 at rtol 1e-6 / atol 1e-12
     desc = like.network.description()
     nominal = np.log10(like.network.param_values[networks.JARM_CALIBRATED])
     return like, desc, like.oracle_protocol(), nominal
