@@ -310,7 +310,7 @@ struct CoopOde {
             }
             b = fma(ih, r, F);
             b2 = fma(ih, r2, F2);
-            Net::solve(M, A, sh.J, inv_d, inv_d2, b, b2, lane, GL == 32 ? 0xffffffffu : gmask, gtm, ltm, sh.sd);
+            Net::solve(M, A, sh.J, inv_d, inv_d2, b, b2, lane, GL == 32 ? 0xffffffffu : gmask, gbase, gtm, ltm, sh.sd);
             if (core) kc[stage * NS] = b;
             if (leaf) kl[stage * NS] = b2;
         }

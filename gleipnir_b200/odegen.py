@@ -348,7 +348,7 @@ class MassActionNetwork(object):
                    "    static __device__ __forceinline__ void solve(const double (&M)[NC], const double (&A)[NXA], "
                    "const double *J, double inv_d,",
                    "                                                 double inv_d2, double &b, double &b2, int lane, "
-                   "unsigned gmask, unsigned gtm, unsigned ltm, double *xs) {",
+                   "unsigned gmask, int gbase, unsigned gtm, unsigned ltm, double *xs) {",
                    pl.cuda_solve(), "    }", "};"]
         return "\n".join(tables + struct)
 

@@ -266,6 +266,10 @@ class CoopPlan(object):
         out.append("        return ok;")
         return "\n".join(out)
 
+    # levels of at most this many columns are broadcast by shuffles instead of shared memory.  Measured on the JARM
+    # network (tools/jarm_check.py, steps/s): 0 -> 7.23e7, 2 -> 7.20e7, 4 -> 7.16e7, 32 (all shuffles) -> 6.23e7.
+    SHUFFLE_LEVEL_WIDTH = int(__import__("os").environ.get("GLEIPNIR_SHFL_WIDTH", "0"))
+
     def xs_stride(self):
         """Doubles per broadcast buffer of the substitution: one slot per lane plus one per leaf."""
         return max(self.gl, self.nc) + max(self.nx, 0)
@@ -293,29 +297,28 @@ class CoopPlan(object):
             out.append("        __syncwarp(gmask);")
             for l in range(nx):
                 out.append("        b = fma(-A[%d], xs[%d], b);" % (l, leaf0 + l))
-        for level in self.fwd_levels:
+        def level_code(cols, mask):
+            # narrow levels (the sequential tail of the elimination: the hub species form a clique) take the
+            # broadcast from a shuffle -- ~25 cycles against ~55 for the store / sync / load round trip
             out.append("        {")
-            out.append("            double *X = xs + buf * XS; buf ^= 1;")
-            out.append("            X[lane] = b;")
-            out.append("            __syncwarp(gmask);")
-            for c in level:
-                out.append("            const double t%d = X[%d];" % (c, c))
-            for c in level:
-                out.append("            if (gtm & %du) b = fma(-M[%d], t%d, b);" % (1 << c, c, c))
+            if len(cols) <= self.SHUFFLE_LEVEL_WIDTH:
+                for c in cols:
+                    out.append("            const double t%d = gl::shfl_f64(gmask, b, gbase + %d);" % (c, c))
+            else:
+                out.append("            double *X = xs + buf * XS; buf ^= 1;")
+                out.append("            X[lane] = b;")
+                out.append("            __syncwarp(gmask);")
+                for c in cols:
+                    out.append("            const double t%d = X[%d];" % (c, c))
+            for c in cols:
+                out.append("            if (%s & %du) b = fma(-M[%d], t%d, b);" % (mask, 1 << c, c, c))
             out.append("        }")
+        for level in self.fwd_levels:
+            level_code(level, "gtm")
         out.append("        b *= inv_d;")
         for scale, bcast in self.bwd_levels:
-            if not bcast:
-                continue
-            out.append("        {")
-            out.append("            double *X = xs + buf * XS; buf ^= 1;")
-            out.append("            X[lane] = b;")
-            out.append("            __syncwarp(gmask);")
-            for c in bcast:
-                out.append("            const double t%d = X[%d];" % (c, c))
-            for c in bcast:
-                out.append("            if (ltm & %du) b = fma(-M[%d], t%d, b);" % (1 << c, c, c))
-            out.append("        }")
+            if bcast:
+                level_code(bcast, "ltm")
         if nx:
             out.append("        {")
             out.append("            double *X = xs + buf * XS; buf ^= 1;")
