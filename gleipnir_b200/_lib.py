@@ -100,6 +100,8 @@ _SIGNATURES = {
     "gl_comm_all_gather_f64": (c_int, [_P, _P, _P, c_int64, _P]),
     "gl_ns_advance_sharded": (c_int, [_P, _P, c_int64, c_int32, c_int64, c_double, _P]),
     "gl_ns_advance_many": (c_int, [_P, c_int32, _P, _P]),
+    "gl_ns_advance_many_graphs": (c_int, [_P, c_int32, _P, _P]),
+    "gl_ns_advance_graph": (c_int, [_P, c_int64, _P]),
     "gl_ns_step_sharded": (c_int, [_P, _P, c_int32, c_int32, c_int64, c_double, _P]),
     "gl_ns_shard_candidate_count": (c_int32, [c_int32, c_int32, c_int64, c_double]),
     "gl_ns_shard_commit_truncated": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),

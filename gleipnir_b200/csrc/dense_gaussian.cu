@@ -32,6 +32,9 @@ __global__ void dense_gaussian_pack_kernel(const double *__restrict__ P, int d, 
     }
 }
 
+// Round 2: a warp owns TWO 8-row tiles at a time and walks the n-tiles in pairs, so four independent accumulator
+// pairs are in flight (a dependent chain of KT DMMAs per pair was the r1 limiter: 27 % of the DMMA peak) and every
+// B fragment fetched from shared memory feeds two DMMAs.
 template <int KTM>
 __global__ void __launch_bounds__(DG_WARPS * 32) dense_gaussian_dmma_kernel(
     const double *__restrict__ x, long long n, int d, int KT, int NT, const double *__restrict__ mu,
@@ -39,39 +42,71 @@ __global__ void __launch_bounds__(DG_WARPS * 32) dense_gaussian_dmma_kernel(
     extern __shared__ double sm[];
     const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;          // padded row length
     double *Ps = sm;                                           // [KT*NT*32]
-    double *Rs_all = Ps + (size_t)KT * NT * 32;                // [DG_WARPS][8][dp]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < KT * NT * 32; e += DG_WARPS * 32) Ps[e] = Pf[e];
+    double *Rs_all = Ps + (size_t)KT * NT * 32;                // [DG_WARPS][16][dp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int e = tid; e < KT * NT * 32; e += blockDim.x) Ps[e] = Pf[e];
     __syncthreads();
-    double *Rs = Rs_all + (size_t)warp * 8 * dp;
+    double *Rs = Rs_all + (size_t)warp * 16 * dp;
     const int grp = lane >> 2, tig = lane & 3;
-    const long long n_tiles = (n + 7) / 8;
-    for (long long t = (long long)blockIdx.x * DG_WARPS + warp; t < n_tiles; t += (long long)gridDim.x * DG_WARPS) {
-        const long long r0 = t * 8;
-        const int rows = (int)((n - r0) < 8 ? (n - r0) : 8);
-        // stage the residual tile (coalesced: rows*d contiguous doubles), zero padding
-        for (int e = lane; e < 8 * dp; e += 32) {
-            const int r = e / dp, c = e - r * dp;
-            Rs[e] = (r < rows && c < d) ? x[(r0 + r) * d + c] - __ldg(mu + c) : 0.0;
+    const long long n_tiles = (n + 15) / 16;
+    for (long long t = (long long)blockIdx.x * nw + warp; t < n_tiles; t += (long long)gridDim.x * nw) {
+        const long long r0 = t * 16;
+        const int rows = (int)((n - r0) < 16 ? (n - r0) : 16);
+        // stage the residual tiles (coalesced: rows*d contiguous doubles), zero padding
+        for (int c = lane; c < dp; c += 32) {                   // lane = column: no index division, rows coalesced
+            const double m = c < d ? __ldg(mu + c) : 0.0;
+#pragma unroll 4
+            for (int r = 0; r < 16; ++r)
+                Rs[r * dp + c] = (r < rows && c < d) ? x[(r0 + r) * d + c] - m : 0.0;
         }
         __syncwarp();
-        double a[KTM];
+        double a0[KTM], a1[KTM];
 #pragma unroll
-        for (int ks = 0; ks < KTM; ++ks) a[ks] = ks < KT ? Rs[grp * dp + ks * 4 + tig] : 0.0;
-        double q = 0.0;
-        for (int nt = 0; nt < NT; ++nt) {
-            double c0 = 0.0, c1 = 0.0;
+        for (int ks = 0; ks < KTM; ++ks) {
+            a0[ks] = ks < KT ? Rs[grp * dp + ks * 4 + tig] : 0.0;
+            a1[ks] = ks < KT ? Rs[(8 + grp) * dp + ks * 4 + tig] : 0.0;
+        }
+        double q0 = 0.0, q1 = 0.0;
+        int nt = 0;
+        for (; nt + 1 < NT; nt += 2) {
+            double c00 = 0.0, d00 = 0.0, c01 = 0.0, d01 = 0.0, c10 = 0.0, d10 = 0.0, c11 = 0.0, d11 = 0.0;
+            const double *B0 = Ps + (size_t)nt * 32 + lane, *B1 = B0 + 32;
 #pragma unroll
             for (int ks = 0; ks < KTM; ++ks)
-                if (ks < KT) dmma_m8n8k4(c0, c1, a[ks], Ps[(ks * NT + nt) * 32 + lane]);
+                if (ks < KT) {
+                    const double b0 = B0[(size_t)ks * NT * 32], b1 = B1[(size_t)ks * NT * 32];
+                    dmma_m8n8k4(c00, d00, a0[ks], b0);
+                    dmma_m8n8k4(c01, d01, a0[ks], b1);
+                    dmma_m8n8k4(c10, d10, a1[ks], b0);
+                    dmma_m8n8k4(c11, d11, a1[ks], b1);
+                }
             // accumulator layout: row = grp, cols = nt*8 + tig*2 + {0,1}
             const int col = nt * 8 + tig * 2;
-            q = fma(c0, Rs[grp * dp + col], q);
-            q = fma(c1, Rs[grp * dp + col + 1], q);
+            const double *R0 = Rs + grp * dp + col, *R1 = Rs + (8 + grp) * dp + col;
+            q0 = fma(c00, R0[0], q0); q0 = fma(d00, R0[1], q0); q0 = fma(c01, R0[8], q0); q0 = fma(d01, R0[9], q0);
+            q1 = fma(c10, R1[0], q1); q1 = fma(d10, R1[1], q1); q1 = fma(c11, R1[8], q1); q1 = fma(d11, R1[9], q1);
         }
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        if (tig == 0 && grp < rows) out[r0 + grp] = -0.5 * q + log_norm;
+        if (nt < NT) {                                          // odd number of n-tiles: the last one alone
+            double c00 = 0.0, d00 = 0.0, c10 = 0.0, d10 = 0.0;
+            const double *B0 = Ps + (size_t)nt * 32 + lane;
+#pragma unroll
+            for (int ks = 0; ks < KTM; ++ks)
+                if (ks < KT) {
+                    const double b0 = B0[(size_t)ks * NT * 32];
+                    dmma_m8n8k4(c00, d00, a0[ks], b0);
+                    dmma_m8n8k4(c10, d10, a1[ks], b0);
+                }
+            const int col = nt * 8 + tig * 2;
+            const double *R0 = Rs + grp * dp + col, *R1 = Rs + (8 + grp) * dp + col;
+            q0 = fma(c00, R0[0], q0); q0 = fma(d00, R0[1], q0);
+            q1 = fma(c10, R1[0], q1); q1 = fma(d10, R1[1], q1);
+        }
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        if (tig == 0 && grp < rows) out[r0 + grp] = -0.5 * q0 + log_norm;
+        if (tig == 0 && 8 + grp < rows) out[r0 + 8 + grp] = -0.5 * q1 + log_norm;
         __syncwarp();
     }
 }
@@ -80,8 +115,11 @@ int dense_gaussian_eval_launch(const gl_model *m, const double *x, long long n, 
     const int d = m->dev.d;
     const int KT = (d + 3) / 4, NT = (d + 7) / 8;
     const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;
-    const int smem = (int)(sizeof(double) * ((size_t)KT * NT * 32 + (size_t)DG_WARPS * 8 * dp));
-    long long blocks = ((n + 7) / 8 + DG_WARPS - 1) / DG_WARPS;
+    int warps = DG_WARPS;                                      // fewer warps per block when P itself fills shared memory
+    while (warps > 1 && sizeof(double) * ((size_t)KT * NT * 32 + (size_t)warps * 16 * dp) > 200 * 1024) warps >>= 1;
+    const int smem = (int)(sizeof(double) * ((size_t)KT * NT * 32 + (size_t)warps * 16 * dp));
+    GL_REQUIRE(smem <= 227 * 1024, "dense Gaussian: d=%d does not fit the tensor-core kernel's shared memory", d);
+    long long blocks = ((n + 15) / 16 + warps - 1) / warps;
     const long long cap = (long long)sm_count() * 2;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -90,7 +128,7 @@ int dense_gaussian_eval_launch(const gl_model *m, const double *x, long long n, 
         if (smem > 48 * 1024)                                                                                    \
             GL_CUDA(cudaFuncSetAttribute(dense_gaussian_dmma_kernel<KTM>,                                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
-        dense_gaussian_dmma_kernel<KTM><<<(int)blocks, DG_WARPS * 32, smem, st>>>(                               \
+        dense_gaussian_dmma_kernel<KTM><<<(int)blocks, warps * 32, smem, st>>>(                               \
             x, n, d, KT, NT, m->dev.aux0, m->dev.aux2, m->dev.s0, out);                                          \
     } while (0)
     if (KT <= 4) GL_DG_LAUNCH(4);

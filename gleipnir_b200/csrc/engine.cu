@@ -1786,6 +1786,7 @@ __global__ void __launch_bounds__(EXPORT_THREADS) export_gathered_kernel(
 
 // ============================== host side / C ABI ==========================================
 struct gl_ns {
+    cudaGraphExec_t graph_exec = nullptr;         // gl_ns_advance_graph: kept until the next capture / destroy
     gl_ns_config cfg;
     int d;
     gl::ModelDev model;
@@ -2147,8 +2148,32 @@ int gl_ns_destroy(gl_ns *ns) {
     if (ns) {
         for (cudaEvent_t e : ns->ev_walk) cudaEventDestroy(e);
         for (cudaEvent_t e : ns->ev_sel) cudaEventDestroy(e);
+        if (ns->graph_exec) cudaGraphExecDestroy(ns->graph_exec);
     }
     delete ns;
+    return GL_OK;
+}
+
+// gl_ns_advance recorded into a CUDA graph and launched as one unit: the launch sequence of a run with a closed-form
+// death count involves no host decision, so the ~4 launches per step (programmatic-dependent-launch edges included)
+// can be replayed by the device front end instead of being issued one by one from a host thread.  Used by
+// gl_ns_advance_many, where the host's launch rate is what limits concurrent runs.
+int gl_ns_advance_graph(gl_ns *ns, int64_t n_deaths_total, void *stream) {
+    GL_REQUIRE(ns != nullptr, "ns is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    GL_REQUIRE(st != nullptr, "graph capture needs a non-default stream");
+    GL_REQUIRE(!ns->prof, "per-kernel profiling events cannot be captured");
+    if (ns->graph_exec) { cudaGraphExecDestroy(ns->graph_exec); ns->graph_exec = nullptr; }
+    GL_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = gl_ns_advance(ns, n_deaths_total, stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != GL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return gl::cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    const cudaError_t e2 = cudaGraphInstantiate(&ns->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return gl::cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
+    GL_CUDA(cudaGraphLaunch(ns->graph_exec, st));
     return GL_OK;
 }
 
@@ -2257,7 +2282,19 @@ int gl_ns_advance(gl_ns *ns, int64_t n_deaths_total, void *stream) {
 // thread per engine enqueues that engine's whole run on its own stream, so the launches of the runs interleave and
 // their kernels overlap on the device -- a single small run offers a few tens of thousands of threads to a machine
 // with 3*10^5 of them (HypSelector.run_nested_sampling runs its models one after another, hyp_selector.py:236-248).
+static int advance_many_impl(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams, bool graphs);
+
 int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams) {
+    return advance_many_impl(engines, n, n_deaths_total, streams, false);
+}
+
+int gl_ns_advance_many_graphs(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams) {
+    return advance_many_impl(engines, n, n_deaths_total, streams, true);
+}
+
+}  // extern "C"
+
+static int advance_many_impl(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams, bool graphs) {
     GL_REQUIRE(engines != nullptr && streams != nullptr && n_deaths_total != nullptr && n >= 1, "bad argument");
     for (int i = 0; i < n; ++i) GL_REQUIRE(engines[i] != nullptr, "engine %d is NULL", i);
     int dev = 0;
@@ -2269,7 +2306,8 @@ int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total
     for (int i = 0; i < n; ++i)
         threads.emplace_back([&, i]() {
             cudaSetDevice(dev);
-            rcs[(size_t)i] = gl_ns_advance(engines[i], n_deaths_total[i], streams[i]);
+            rcs[(size_t)i] = graphs ? gl_ns_advance_graph(engines[i], n_deaths_total[i], streams[i])
+                                    : gl_ns_advance(engines[i], n_deaths_total[i], streams[i]);
             if (rcs[(size_t)i] != GL_OK) msgs[(size_t)i] = gl::error_buffer();
         });
     for (auto &t : threads) t.join();
@@ -2280,6 +2318,8 @@ int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total
         }
     return GL_OK;
 }
+
+extern "C" {
 
 int gl_ns_finalize(gl_ns *ns, void *stream) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");

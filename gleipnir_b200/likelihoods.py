@@ -47,7 +47,7 @@ class DeviceLogLikelihood(object):
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h is not None and _lib._lib is not None:
+        if h is not None and _lib is not None and getattr(_lib, "_lib", None) is not None:
             try:
                 _lib._lib.gl_model_destroy(h)
             except Exception:

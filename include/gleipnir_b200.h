@@ -217,6 +217,11 @@ GL_API int gl_ns_inject(gl_ns *ns, const double *points_dev, const double *logl_
  * concurrently: one host thread per engine enqueues on streams[i], so the runs' kernels overlap on the device.
  * Per-engine results are identical to n separate gl_ns_advance calls. */
 GL_API int gl_ns_advance_many(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams);
+/* The same with every run recorded into a CUDA graph first (gl_ns_advance_graph) and launched as one unit: the
+ * device front end replays the launches, so the host's launch rate stops limiting concurrent runs.  Streams must
+ * be non-default; engines must not have per-kernel profiling enabled. */
+GL_API int gl_ns_advance_many_graphs(gl_ns **engines, int32_t n, const int64_t *n_deaths_total, void **streams);
+GL_API int gl_ns_advance_graph(gl_ns *ns, int64_t n_deaths_total, void *stream);
 GL_API int gl_ns_finalize(gl_ns *ns, void *stream);
 
 /* `dead_points` (nested_sampling.py:211,338-344) assembled on the device: table_dev[n_rows, d+2]
