@@ -50,7 +50,7 @@ class MassActionNetwork(object):
                 sf = float(r[3])
             else:
                 sf = 1.0
-                for sp in set(reac):
+                for sp in sorted(set(reac)):
                     sf /= math.factorial(reac.count(sp))
             self.reactions.append((rate, reac, prod, sf))
         self.initials = dict(initials)
@@ -111,7 +111,7 @@ class MassActionNetwork(object):
         lines.append("    static __device__ __forceinline__ void jac(const double *y, const double *p, double *J) {")
         dv = {}
         for i, (k, reac, prod, sf) in enumerate(self.reactions):
-            for q in set(reac):
+            for q in sorted(set(reac)):            # sorted: the generated text (and its hash) must not depend on PYTHONHASHSEED
                 m = reac.count(q)
                 others = list(reac)
                 others.remove(q)                      # d/dy_q of y_q^m = m*y_q^(m-1)
@@ -200,7 +200,7 @@ class MassActionNetwork(object):
         f_lists = [[] for _ in range(ns)]                    # per internal species: sv indices
         j_lists = [dict() for _ in range(ns)]                # per internal species: {column: [sd indices]}
         for r, (k, reac, prod, sf) in enumerate(self.reactions):
-            for name in set(reac) | set(prod):
+            for name in sorted(set(reac) | set(prod)):
                 net = prod.count(name) - reac.count(name)
                 if not net:
                     continue

@@ -35,10 +35,10 @@ def jacobian_pattern(network):
     P = np.zeros((ns, ns), dtype=bool)
     for k, reac, prod, sf in network.reactions:
         rows = set()
-        for s in set(reac) | set(prod):
+        for s in sorted(set(reac) | set(prod)):
             if prod.count(s) - reac.count(s) != 0:
                 rows.add(network._sp(s))
-        for q in set(reac):
+        for q in sorted(set(reac)):
             for s in rows:
                 P[s, network._sp(q)] = True
     return P

@@ -206,3 +206,18 @@ def test_cooperative_plugin_exports_counters():
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
     assert "DFMA" in sass and "SHFL.IDX" in sass
+
+
+def test_generated_sources_do_not_depend_on_the_hash_seed():
+    """The plugin file name is a hash of the generated source: it must be the same in every process, or the prebuilt
+    plugins shipped to the GPU box are ignored and rebuilt there."""
+    import sys
+    code = ("from gleipnir_b200 import networks; "
+            "print([mk().source_hash() for mk in networks.SHIPPED.values()])")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = set()
+    for seed in ("0", "1", "77"):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        outs.add(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True, cwd=here,
+                                env=env).stdout.strip())
+    assert len(outs) == 1, outs
