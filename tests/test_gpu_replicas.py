@@ -96,3 +96,28 @@ def test_model_selection_sweep(cuda, golden_dir):
     alone = NestedSampleIt(networks.dimerization(), {"A_dimer": (data, 10.0 * sd, None)}, ts)(
         'built-in', ns_population_size=100, ns_kwargs=dict(seed=5))
     assert alone.run() == (sel.nested_samplers[0].log_evidence, sel.nested_samplers[0].log_evidence_error)
+
+
+def test_graph_recorded_run_equals_the_directly_launched_run(cuda):
+    """gl_ns_advance_graph: the whole run recorded into a CUDA graph (programmatic-dependent-launch edges included)
+    and launched as one unit gives the bit-identical run."""
+    import torch
+    from gleipnir_b200 import _lib as L
+    from gleipnir_b200.engine import DeviceEngine
+    from gleipnir_b200.likelihoods import EggCartonLogLikelihood
+    lib = L.load()
+    table = [(L.GL_PRIOR_UNIFORM, 0.0, 10.0 * np.pi)] * 2
+    like = EggCartonLogLikelihood(2)
+    out = []
+    for graph in (False, True):
+        eng = DeviceEngine(table, like, 2000, 200, 12000, iterations=8, tuning_cycles=2, seed=6, stream=torch.cuda.Stream())
+        torch.cuda.synchronize()
+        eng.init()
+        if graph:
+            L.check(lib.gl_ns_advance_graph(eng._h, 12000, eng._stream()))
+        else:
+            eng.advance(12000)
+        eng.finalize()
+        st = eng.state()
+        out.append((st.log_z, st.information, st.n_evals, eng.dead_table()[0]))
+    assert out[0][:3] == out[1][:3] and np.array_equal(out[0][3], out[1][3])
