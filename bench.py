@@ -9,8 +9,8 @@ NestedSampleIt configures for the built-in sampler (nestedsample_it.py:416-427).
 
 A "step" is ONE Nested Sampling batch of the running C5 run: the k worst live points die (selection,
 evidence / information update, dead-row record) and k walkers refill them, each doing 20*d tuning
-+ 20*d production trial moves = 721 likelihood evaluations of 4 stiff ODE solves.  k = 800 per GPU
-(one resident wave of the walker kernel).  A converged C5 run is ~4*10^3 such steps (hours), so it is
++ 20*d production trial moves = 721 likelihood evaluations of 4 stiff ODE solves.  k = one resident wave of the
+walker kernel per GPU (148 SMs x 4 blocks x 2 walkers = 1184; sharded runs keep 3.5 sigma of headroom).  A converged C5 run is ~4*10^3 such steps (hours), so it is
 not a bench step; the converged-run figures carried on the same line are C2 (eggcarton, N = 10^4) and
 C3 (50-D dense Gaussian, N = 10^6) as `secondary`.
 
@@ -38,7 +38,17 @@ sys.path.insert(0, ROOT)
 C5 = dict(name="C5 JARM ODE likelihood (synthetic JARM-shaped network: 34 species, 84 reactions, 18 sampled of 50 "
                "parameters; 2 conditions x (pre-equilibration + 181-time solve), 5 data terms + 4 cycle terms), "
                "N=1e5 live points, one NS batch per step",
-          population=100000, k_per_gpu=800, iterations=10, burn_in=10, tuning_cycles=1, d=18)
+          population=100000, iterations=10, burn_in=10, tuning_cycles=1, d=18)
+
+
+def c5_walkers_per_gpu(like, world):
+    """One resident wave of walk_coop_kernel: SMs x resident blocks per SM x 2 walkers per 128-thread block (a walker =
+    one warp per condition).  Sharded runs keep 3.5 sigma of headroom: a rank's share of a step's k*world deaths is
+    Binomial, and walkers beyond the resident wave would run as a second wave."""
+    import math
+    from gleipnir_b200 import _lib
+    cap = _lib.device_info()[0] * like.network.coop_min_blocks() * 2
+    return cap if world == 1 else int(cap - 3.5 * math.sqrt(cap))
 
 C2 = dict(name="C2 eggcarton d=2 N=1e4/GPU RemainingPriorMass(1e-6)", d=2, population=10000,
                 iterations=50, burn_in=0, tuning_cycles=2, cutoff=1e-6, truth_logz=235.88)
@@ -343,12 +353,13 @@ def run_c5(args, env):
     from gleipnir_b200.sharded import shard_bounds
     w = C5
     d, N = w["d"], w["population"]
-    k = (args.batch_k if args.batch_k else w["k_per_gpu"]) * world
     like = jarm.jarm_loglikelihood()
+    k = (args.batch_k if args.batch_k else c5_walkers_per_gpu(like, world)) * world
     table = [(L.GL_PRIOR_UNIFORM, a, b) for a, b in jarm.jarm_prior_table()]
     n_steps = args.warmup + args.steps
     skw = dict(iterations=w["iterations"], burn_in=w["burn_in"], tuning_cycles=w["tuning_cycles"], proposal=0, seed=2024)
     cap = (n_steps + 2) * k
+    n_prof = 1                                              # extra step(s) with events around every walker launch
     if world > 1:
         off, n_loc = shard_bounds(N, world, rank)
         eng = DeviceEngine(table, like, n_loc, k, cap, row_offset=off, global_population=N, **skw)
@@ -397,7 +408,7 @@ def run_c5(args, env):
     launches_per_step = w["tuning_cycles"] + 1 + 1          # walker phases + the kill / fused sharded step
     # per-kernel time for the roofline: events around every walker launch, in 2 extra steps
     eng.profile_enable(True)
-    for i in range(n_steps, n_steps + 2):
+    for i in range(n_steps, n_steps + n_prof):
         advance((i + 2) * k, (i + 1) * k)
     torch.cuda.synchronize()
     walk_ms, walk_launches, sel_ms, sel_launches = eng.profile_read()
@@ -409,7 +420,7 @@ def run_c5(args, env):
     return dict(like=like, eng=eng, k=k, N=N, t_dev=t_dev, evals=evals, solves=solves, ode_steps=steps_ode,
                 nominal_evals=nominal_evals, clocks=clk, t_init=t_init, launches=args.steps * launches_per_step * world,
                 walk_ms=walk_ms, walk_launches=walk_launches, sel_ms=sel_ms, sel_launches=sel_launches,
-                ctr_prof=ctr_prof, state=st, ms_steps=times)
+                ctr_prof=ctr_prof, state=st, ms_steps=times, n_prof=n_prof)
 
 
 def run_c5_e2e(args, env, k):
@@ -654,9 +665,9 @@ def run_b200_arm(args):
                     solves_per_eval=c5["solves"] / max(c5["evals"], 1),
                     rhs_evals_per_s=6.0 * steps_prof / walk_s if walk_s > 0 else None,
                     avg_launch_ms=c5["walk_ms"] / max(c5["walk_launches"], 1), launches_timed=int(c5["walk_launches"]),
-                    walker_share_of_step=c5["walk_ms"] / 2.0 / step_ms,
+                    walker_share_of_step=c5["walk_ms"] / c5["n_prof"] / step_ms,
                     select_avg_launch_us=1e3 * c5["sel_ms"] / max(c5["sel_launches"], 1),
-                    timing="CUDA events around every walker launch in 2 extra steps after the timed region",
+                    timing="CUDA events around the walker launches of %d extra step(s) after the timed region" % c5["n_prof"],
                     note="latency-bound: a walker is a chain of 721 dependent likelihood evaluations, each 2 x (pre-equilibration "
                          "+ main) stiff solves of ~10^2-10^3 dependent Rosenbrock steps; fp64 pipe utilisation and stall "
                          "reasons from ncu are in profiles/r02_*")
@@ -679,7 +690,7 @@ def run_b200_arm(args):
                                         "-inf phase ends: 59 % of the prior box lies outside the half-normal term's support)",
                             l2="flushed between timed steps (256 MB memset)",
                             parallelism=("live set sharded over %d ranks (N/world each); per step one fused kernel exchanges the "
-                                         "candidate logL over NVLink peer memory; k = 800 walkers per GPU (weak in k)" % world)
+                                         "candidate logL over NVLink peer memory; k = %d walkers per GPU (weak in k)" % (world, c5["k"] // world))
                             if world > 1 else "single"),
                 clocks=c5["clocks"], gpu_launches=int(c5["launches"]), e2e=e2e, roofline=roofline, cpu_baseline=cpu,
                 time_to_converged_logZ_s=None,
@@ -749,7 +760,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-k", type=int, default=0, help="C5 walkers per GPU per step (default 800)")
+    ap.add_argument("--batch-k", type=int, default=0,
+                    help="C5 walkers per GPU per step (default: one resident wave, 1184 on a 148-SM part)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     args = ap.parse_args()

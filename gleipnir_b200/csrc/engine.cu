@@ -2017,7 +2017,7 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
         }
         GL_CHECK_LAUNCH();
         prof_mark(ns, ns->ev_sel, st);
-        ns->prof_sel_launches += 1;
+        if (ns->prof) ns->prof_sel_launches += 1;
         ns->h_launches += 1;
     } else {
         int rcf = flush_end_walk(ns, st);
@@ -2027,7 +2027,7 @@ static int kill_launch(gl_ns *ns, int k_req, long long n_target, cudaStream_t st
         int rc = select_launch(ns->buf.logl, N, &ns->S->k_cur, 0, 0, ns->dead_list, nullptr, ns->is_dead, ns->sel, st);
         if (rc) return rc;
         prof_mark(ns, ns->ev_sel, st);
-        ns->prof_sel_launches += SEL_PASSES + 2;
+        if (ns->prof) ns->prof_sel_launches += SEL_PASSES + 2;
         ns->h_launches += 1 + SEL_PASSES + 2 + 2;     // begin + select + record + accumulate
         record_kernel<<<blocks_for((long long)k_req * ns->d, 256, 8), 256, 0, st>>>(
             ns->S, ns->dead_list, ns->buf.live, ns->buf.logl, ns->d, ns->cfg.row_offset, log(n_global + 1.0),
@@ -2063,7 +2063,7 @@ static int refill_launch(gl_ns *ns, cudaStream_t st) {
     ns->book_deferred = false;
     if (rc) return rc;
     prof_mark(ns, ns->ev_walk, st);
-    ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
+    if (ns->prof) ns->prof_walk_launches += ns->cfg.tuning_cycles + 1;
     ns->h_launches += ns->cfg.tuning_cycles + 1;
     if (ns->defer_ok && next_op_folds_end_walk(ns)) {
         ns->end_walk_deferred = true;      // the next fused kill / candidates kernel finishes this refill
@@ -2444,7 +2444,7 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
                                ns->cand_list, cand_logl_dev));
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
-        ns->prof_sel_launches += 1;
+        if (ns->prof) ns->prof_sel_launches += 1;
         ns->h_launches += 1;
         return GL_OK;
     }
@@ -2453,7 +2453,7 @@ int gl_ns_shard_candidates(gl_ns *ns, int32_t k, double *cand_logl_dev, void *st
     rc = gl::select_launch(ns->buf.logl, N, nullptr, k, 0, ns->cand_list, nullptr, nullptr, ns->sel, st);
     if (rc) return rc;
     gl::prof_mark(ns, ns->ev_sel, st);
-    ns->prof_sel_launches += gl::SEL_PASSES + 2;
+    if (ns->prof) ns->prof_sel_launches += gl::SEL_PASSES + 2;
     gl::shard_gather_kernel<<<gl::blocks_for(k, 256, 4), 256, 0, st>>>(ns->cand_list, ns->buf.logl, k, cand_logl_dev);
     GL_CHECK_LAUNCH();
     ns->h_launches += gl::SEL_PASSES + 2 + 1;
@@ -2527,7 +2527,7 @@ int gl_ns_shard_commit_truncated(gl_ns *ns, const double *gathered_logl_dev, int
         ns->walk_k_max = m;
         GL_CHECK_LAUNCH();
         gl::prof_mark(ns, ns->ev_sel, st);
-        ns->prof_sel_launches += 1;
+        if (ns->prof) ns->prof_sel_launches += 1;
         ns->h_launches += 1;
         ns->h_n_dead += k;
         ns->h_k_last = -1;
@@ -2585,7 +2585,7 @@ int gl_ns_internal_shard_step_p2p(gl_ns *ns, const gl::PeerTables *tables, int32
                            (long long *)ns->buf.dead_idx, ns->buf.dead_step, defer_book ? 1 : 0,
                            gl::peer_timeout_ns_host()));
     gl::prof_mark(ns, ns->ev_sel, st);
-    ns->prof_sel_launches += 1;
+    if (ns->prof) ns->prof_sel_launches += 1;
     ns->h_launches += 1;
     ns->h_n_dead += k;
     ns->h_k_last = -1;
@@ -2736,6 +2736,13 @@ int gl_ns_force_smem_walker(gl_ns *ns, int32_t enable) {
 
 int gl_ns_profile_enable(gl_ns *ns, int32_t enable) {
     GL_REQUIRE(ns != nullptr, "ns is NULL");
+    if (enable && !ns->prof) {                       // a new measurement window: drop what an earlier one left
+        for (cudaEvent_t e : ns->ev_walk) cudaEventDestroy(e);
+        for (cudaEvent_t e : ns->ev_sel) cudaEventDestroy(e);
+        ns->ev_walk.clear();
+        ns->ev_sel.clear();
+        ns->prof_walk_launches = ns->prof_sel_launches = 0;
+    }
     ns->prof = enable != 0;
     return GL_OK;
 }

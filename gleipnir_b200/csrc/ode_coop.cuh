@@ -101,6 +101,16 @@ __device__ __forceinline__ double pfma_lt(int lane, int c, double m, double t, d
         : "+d"(b) : "r"(lane), "r"(c), "d"(m), "d"(t));
     return b;
 }
+// 1/x from the hardware's 20-bit seed (MUFU.RCP64H) and two Newton steps: ~1 ulp, no slow path, half the
+// instructions of the IEEE division -- the elimination takes one reciprocal per pivot on its critical path
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 // b * s on the lanes of `mask`, else b
 __device__ __forceinline__ double pmul_mask(int lane, unsigned mask, double b, double s) {
     asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshr.b32 t, %2, %1;\n\tand.b32 t, t, 1;\n\tsetp.ne.b32 p, t, 0;\n\t@p mul.rn.f64 %0, %0, %3;\n\t}"
@@ -115,15 +125,19 @@ struct CoopCounters {
     unsigned long long next;          // work-claim cursor of the batch-evaluation kernel (zeroed before a launch)
 };
 
-// Net (generated): NS, NC (core rows), NX (leaves), NXA = max(NX,1), NP, NR, NOBS, GL, LD (row stride of J:
-// >= NS, = 2 mod 4), NRM = ceil(NR/GL), NRP = NRM*GL, EF/EF2/EJ/EJ2 (list depths);
+// Net (generated): NS, NC (core rows), NX (leaves), NXA = max(NX,1), NP, NR, NOBS, GL, LD (row stride of the leaf
+// rows of J), NRM = ceil(NR/GL), NRP = NRM*GL, EF/EF2/ED/EM/EJ2 (list depths);
 // all species indices in the plan's INTERNAL numbering (core 0..NC-1, leaves NC..NS-1);
 //   rx_k(r) (rate parameter), rx_sf(r) (double)
 //   rtab(r)   = a | b << 16: reactant slots of reaction r in y[] (y[NS] = 1.0 stands in for "no second reactant")
 //   ftab(e*GL + i)            position in sv[] of the e-th term of f_i (padding: the zero slot 2*NRP)
-//   jtab(e*GL + i)            position in sd[] | column << 16 | "first term of this J_i,column" << 24; every entry
-//                             stores the running sum, so the last store of a column holds the full sum
-//   ftab2 / jtab2             the same for the leaf species (width NXA)
+//   dtab(e*GL + i)            position in sd[] of the e-th term of -J_ii (padding: the zero slot 4*NRP)
+//   mtab(z*GL + i)            column lists of M = diag*I - J: load_m() sums sd[mtab(..)] per column into the register
+//                             row; the diagonal entry is the lane's own slot sd[4*NRP + 2 + i]
+//   ftab2                     ftab for the leaf species (width NXA)
+//   jtab2(e*NXA + l)          leaf ROWS (kept in shared memory): position in sd[] | column << 16 | "first term of
+//                             this J_l,column" << 24; every entry stores the running sum
+//   load_m(M, A, sd, mtab, lane)
 //   init_kind(i) (0 const, 1 parameter), init_val(i) (double), init_par(i)
 //   obs_ptr(o), obs_sp(z), obs_coef(z) (double)
 //   lu(M, A, J, diag, lane, gmask, gbase, inv_d2) -> pivots ok;  solve(M, A, J, inv_d, inv_d2, b, b2, ...)
@@ -131,23 +145,25 @@ template <class Net>
 struct CoopOde {
     static constexpr int NS = Net::NS, NC = Net::NC, NX = Net::NX, NXA = Net::NXA, GL = Net::GL, NR = Net::NR;
     static constexpr int LD = Net::LD, NRM = Net::NRM, NRP = Net::NRP, XS = Net::XS;
-    static constexpr int SD = (4 * NRP + 2 > 2 * XS ? 4 * NRP + 2 : 2 * XS);
+    static constexpr int DG = 4 * NRP + 2;              // sd[DG + lane] = diag - J_ii of the lane's species
+    static constexpr int SD = (DG + GL > 2 * XS ? DG + GL : 2 * XS);
 
     struct alignas(16) Tables {         // per block, in shared memory: the network's index lists
         unsigned int rtab[NRP];
-        unsigned int jtab[Net::EJ * GL];
         unsigned int jtab2[Net::EJ2 * NXA];
         unsigned short ftab[Net::EF * GL];
+        unsigned short mtab[Net::EM * GL];
+        unsigned short dtab[Net::ED * GL];
         unsigned short ftab2[Net::EF2 * NXA];
     };
     struct alignas(16) Shared {         // per group, in shared memory
-        double J[NS * LD];              // Jacobian rows; entries outside the structural pattern stay 0
+        double J[NXA * LD];             // Jacobian rows of the LEAF species; entries outside the pattern stay 0
         double sv[2 * NRP + 2];         // v_r, -v_r; [2*NRP] = 0
-        double sd[SD];                  // dv_r/dy_a, -, dv_r/dy_b, -; [4*NRP] = 0.  Dead once the Jacobian rows are
-                                        // assembled: the substitutions use it as their two broadcast buffers
+        double sd[SD];                  // dv_r/dy_a, -, dv_r/dy_b, -; [4*NRP] = 0; [DG + lane] = diag - J_ii.  Dead once
+                                        // the matrix row is in registers: the substitutions use it as their two
+                                        // broadcast buffers
         double c[NRP];                  // sf_r * p[k_r] of the running solve (0 for the padding reactions)
         double k[6 * NS];               // stage vectors of the running step
-        double dump[2];                 // store target of the lanes that own no Jacobian row
         double y[NS + 2];               // state broadcast; y[NS] = 1
         double p[Net::NP];              // parameter vector of the running solve (overrides applied)
         double pb[Net::NP];             // parameter vector of the evaluation (params[mask] = 10**Y)
@@ -156,13 +172,14 @@ struct CoopOde {
 
     static __device__ __forceinline__ void load_tables(Tables &T) {         // whole block
         for (int i = threadIdx.x; i < NRP; i += blockDim.x) T.rtab[i] = Net::rtab(i);
-        for (int i = threadIdx.x; i < Net::EJ * GL; i += blockDim.x) T.jtab[i] = Net::jtab(i);
+        for (int i = threadIdx.x; i < Net::EM * GL; i += blockDim.x) T.mtab[i] = Net::mtab(i);
+        for (int i = threadIdx.x; i < Net::ED * GL; i += blockDim.x) T.dtab[i] = Net::dtab(i);
         for (int i = threadIdx.x; i < Net::EJ2 * NXA; i += blockDim.x) T.jtab2[i] = Net::jtab2(i);
         for (int i = threadIdx.x; i < Net::EF * GL; i += blockDim.x) T.ftab[i] = Net::ftab(i);
         for (int i = threadIdx.x; i < Net::EF2 * NXA; i += blockDim.x) T.ftab2[i] = Net::ftab2(i);
     }
     static __device__ __forceinline__ void init_shared(Shared &sh, int lane, unsigned gmask) {   // one group
-        for (int i = lane; i < NS * LD; i += GL) sh.J[i] = 0.0;
+        for (int i = lane; i < NXA * LD; i += GL) sh.J[i] = 0.0;
         if (lane == 0) {
             sh.sv[2 * NRP] = sh.sv[2 * NRP + 1] = 0.0;
             sh.sd[4 * NRP] = sh.sd[4 * NRP + 1] = 0.0;
@@ -218,19 +235,11 @@ struct CoopOde {
         __syncwarp(gmask);
     }
 
-    // structural nonzeros of this lane's Jacobian rows (derivative table must be current); branch-free
-    static __device__ __forceinline__ void jac_rows(Shared &sh, const Tables &T, int lane) {
-        double acc = 0.0;
-        double *row = lane < NC ? sh.J + lane * LD : sh.dump;
-#pragma unroll
-        for (int e = 0; e < Net::EJ; ++e) {
-            const unsigned int t = T.jtab[e * GL + lane];
-            acc = sh.sd[t & 0xffffu] + ((t >> 24) ? 0.0 : acc);
-            row[(t >> 16) & 0xffu] = acc;
-        }
+    // Jacobian rows of the leaf species (derivative table must be current); lanes < NX
+    static __device__ __forceinline__ void leaf_rows(Shared &sh, const Tables &T, int lane) {
         if (NX > 0 && lane < NX) {
-            acc = 0.0;
-            row = sh.J + (NC + lane) * LD;
+            double acc = 0.0;
+            double *row = sh.J + lane * LD;
 #pragma unroll
             for (int e = 0; e < Net::EJ2; ++e) {
                 const unsigned int t = T.jtab2[e * NXA + lane];
@@ -246,39 +255,27 @@ struct CoopOde {
     static __device__ bool step(Shared &sh, const Tables &T, int lane, unsigned gmask, int gbase, double yi, double y2,
                                 double h, double &ynew, double &ynew2, double &yerr, double &yerr2) {
         const double ih = 1.0 / h, diag = 1.0 / (ROD_GAMMA * h);
-        // ---- Jacobian rows into shared memory, then the core row of M into registers ----------
+        // ---- the lane's row of M = diag*I - J straight into registers -----------------------------
         publish(sh, lane, gmask, yi, y2);
         if (lane == 0) sh.sd[4 * NRP] = sh.sd[4 * NRP + 1] = 0.0;     // (the previous step's substitutions used sd)
         rates<true>(sh, T, lane, gmask);
-        jac_rows(sh, T, lane);
+        {
+            double da = diag, db = 0.0;                  // diag - J_ii into the lane's own slot of the table
+#pragma unroll
+            for (int e = 0; e < Net::ED; ++e) {
+                const double t = sh.sd[T.dtab[e * GL + lane]];
+                if (e & 1) db += t;
+                else da += t;
+            }
+            sh.sd[DG + lane] = da + db;
+        }
+        leaf_rows(sh, T, lane);
         double F, F2;
         rhs_rows(sh, T, lane, F, F2);
         __syncwarp(gmask);
         double M[NC], A[NXA];
-        {
-            // M = diag*I - J: the diagonal is folded in through shared memory (a per-lane select over the
-            // register row makes the compiler spill the row and index it dynamically)
-            double *row = sh.J + (lane < NC ? lane : 0) * LD;                // rows are 16-byte aligned (LD even)
-            const double jd = row[lane < NC ? lane : 0];
-            if (lane < NC) row[lane] = jd - diag;
-#pragma unroll
-            for (int q = 0; q + 1 < NC; q += 2) {
-                const double2 t = *reinterpret_cast<const double2 *>(row + q);
-                M[q] = -t.x;
-                M[q + 1] = -t.y;
-            }
-            if (NC & 1) M[NC - 1] = -row[NC - 1];
-#pragma unroll
-            for (int l = 0; l < NXA; ++l) A[l] = l < NX ? -row[NC + l] : 0.0;
-            if (lane < NC) row[lane] = jd;
-            if (GL > NC) {                                                   // lanes without a row: zero, so they never contribute
-                const bool core = lane < NC;
-#pragma unroll
-                for (int q = 0; q < NC; ++q) M[q] = core ? M[q] : 0.0;
-#pragma unroll
-                for (int l = 0; l < NXA; ++l) A[l] = core ? A[l] : 0.0;
-            }
-        }
+        Net::load_m(M, A, sh.sd, T.mtab, lane);
+        __syncwarp(gmask);                               // sd is reused by the substitutions
         double inv_d = 1.0, inv_d2 = 0.0;
         const bool ok = Net::lu(M, A, sh.J, diag, lane, GL == 32 ? 0xffffffffu : gmask, gbase, inv_d, inv_d2);
         if (!__all_sync(gmask, ok)) return false;
@@ -341,26 +338,42 @@ struct CoopOde {
                 h = hh * 0.1;
                 continue;
             }
-            double e = 0.0;
+            // error norm: weighted RMS over the species, the norm of the reference's solver (VODE behind
+            // ScipyOdeSimulator); GL_COOP_MAX_NORM selects the max norm.  The group reduction and the step-size
+            // factor run in single precision (an error ESTIMATE steering h; identical on every lane)
+            float e = 0.f;
             bool fin = true;
             if (lane < NC) {
-                e = fabs(yerr) / (ctl.atol + ctl.rtol * fmax(fabs(yi), fabs(ynew)));
-                fin = isfinite(ynew) && e == e;
+                const double q = fabs(yerr) / (ctl.atol + ctl.rtol * fmax(fabs(yi), fabs(ynew)));
+                fin = isfinite(ynew) && q == q;
+                e = (float)q;
             }
             if (NX > 0 && lane < NX) {
-                const double e2 = fabs(yerr2) / (ctl.atol + ctl.rtol * fmax(fabs(y2), fabs(ynew2)));
-                fin = fin && isfinite(ynew2) && e2 == e2;
-                e = fmax(e, e2);
+                const double q2 = fabs(yerr2) / (ctl.atol + ctl.rtol * fmax(fabs(y2), fabs(ynew2)));
+                fin = fin && isfinite(ynew2) && q2 == q2;
+#ifdef GL_COOP_MAX_NORM
+                e = fmaxf(e, (float)q2);
+#else
+                e = sqrtf(e * e + (float)q2 * (float)q2);
+#endif
             }
+#ifdef GL_COOP_MAX_NORM
 #pragma unroll
-            for (int o = GL / 2; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(gmask, e, o));
+            for (int o = GL / 2; o > 0; o >>= 1) e = fmaxf(e, __shfl_xor_sync(gmask, e, o));
+#else
+            e = e * e;
+#pragma unroll
+            for (int o = GL / 2; o > 0; o >>= 1) e += __shfl_xor_sync(gmask, e, o);
+            e = sqrtf(e * (1.0f / NS));
+#endif
             fin = __all_sync(gmask, fin);
             if (!fin) {
                 if (hh < 1e-300) return false;
                 h = hh * 0.1;
                 continue;
             }
-            const double fac = e > 0.0 ? fmin(5.0, fmax(0.2, 0.9 * pow(e, -0.25))) : 5.0;
+            // 0.9 e^(-1/4), clamped to [0.2, 5]
+            const double fac = e > 0.f ? (double)fminf(5.0f, fmaxf(0.2f, 0.9f * rsqrtf(sqrtf(e)))) : 5.0;
             if (e <= 1.0) {
                 yi = ynew;
                 y2 = ynew2;

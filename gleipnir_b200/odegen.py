@@ -156,12 +156,13 @@ class MassActionNetwork(object):
         return self.ns >= self.COOP_MIN_SPECIES
 
     def coop_min_blocks(self):
-        """Resident blocks per SM the cooperative kernels are compiled for: 4 while the register row is at
-        most 16 wide, 3 for a 32-wide row (168 registers: no spills of the matrix row)."""
+        """Resident 128-thread blocks per SM the cooperative kernels are compiled for: 4 (128 registers per thread,
+        16 warps per SM).  The matrix row is gathered straight into registers, so a block of four JARM-size systems
+        needs ~40 KB of shared memory and the register file is the only limit."""
         env = os.environ.get("GLEIPNIR_COOP_MIN_BLOCKS")
         if env:
             return int(env)
-        return 4 if self.plan().nc <= 16 else 3
+        return 4
 
     def plan(self):
         """Elimination plan of the cooperative solver (odeplan.CoopPlan), cached."""
@@ -177,9 +178,14 @@ class MassActionNetwork(object):
 
           sv[2r], sv[2r+1]            = v_r, -v_r                      (reaction rates, both signs)
           sd[4r .. 4r+3]              = dv_r/dy_a, -dv_r/dy_a, dv_r/dy_b, -dv_r/dy_b
+          sd[DG + i]                  = diag - J_ii, written by lane i from its own list dtab[.][i]
 
-        so that  f_i = sum of sv[ftab[e][i]]  and  J_iq = sum of sd[...] over the entries of a segment of
-        jtab[.][i]  -- loads with addresses known up front and adds, no per-entry decoding of the network."""
+        so that  f_i = sum of sv[ftab[e][i]]  and the register row of  M = diag*I - J  is gathered COLUMN BY COLUMN:
+        M[q] of lane i = sum over e < depth_q of sd[mtab[(off_q + e)][i]]  (the opposite-sign slots, so no negation;
+        the diagonal entry points at the lane's own slot DG + i; lanes without an entry in a column point at the
+        zero slot) -- loads with addresses known up front and adds, no per-entry decoding of the network, and no
+        Jacobian rows in shared memory for the core species.  Only the few LEAF rows are stored (jtab2: position in
+        sd | column << 16 | "first term of this sum" << 24), because every lane reads them during the elimination."""
         pl = self.plan()
         gl, nc, nx, ns = pl.gl, pl.nc, pl.nx, self.ns
         inv = pl.inv
@@ -240,13 +246,27 @@ class MassActionNetwork(object):
         nxa = max(nx, 1)
         ef, ftab = ftable(list(range(nc)), gl)
         ef2, ftab2 = ftable(list(range(nc, ns)), nxa)
-        ej, jtab = jtable(list(range(nc)), gl)
         ej2, jtab2 = jtable(list(range(nc, ns)), nxa)
-        ld = ns
-        while ld % 4 != 2:                                   # 16-byte aligned rows whose 128-bit loads spread over the banks
-            ld += 1
-        return dict(nrm=nrm, nrp=nrp, rtab=rtab, ef=ef, ftab=ftab, ef2=ef2, ftab2=ftab2, ej=ej, jtab=jtab, ej2=ej2,
-                    jtab2=jtab2, ld=ld, gl=gl, nc=nc, nx=nx, nxa=nxa, ns=ns)
+        # M = diag*I - J gathered by column: the sign of every term is flipped (index ^ 1)
+        DG = 4 * nrp + 2                                     # per-lane slots holding diag - J_ii
+        ed = max([len(j_lists[i].get(i, [])) for i in range(nc)] + [1])
+        dtab = [ZD] * (ed * gl)
+        for i in range(nc):
+            for e, idx in enumerate(j_lists[i].get(i, [])):
+                dtab[e * gl + i] = idx ^ 1
+        mcols, mtab = [], []                                 # per column of [core | leaf]: (offset, depth)
+        for q in range(ns):
+            per_lane = [([DG + i] if i == q else [idx ^ 1 for idx in j_lists[i].get(q, [])]) if i < nc else []
+                        for i in range(gl)]
+            depth = max(len(t) for t in per_lane)
+            mcols.append((len(mtab) // gl, depth))
+            for e in range(depth):
+                mtab += [t[e] if e < len(t) else ZD for t in per_lane]
+        if not mtab:
+            mtab = [ZD] * gl
+        ld = ns + (ns & 1)
+        return dict(nrm=nrm, nrp=nrp, rtab=rtab, ef=ef, ftab=ftab, ef2=ef2, ftab2=ftab2, ej2=ej2, jtab2=jtab2,
+                    ed=ed, dtab=dtab, mtab=mtab, mcols=mcols, dg=DG, ld=ld, gl=gl, nc=nc, nx=nx, nxa=nxa, ns=ns)
 
     def emulate_rhs_jac(self, y, p):
         """f and J (ORIGINAL numbering) computed the way the device does, from coop_tables(); CPU tests compare
@@ -260,7 +280,7 @@ class MassActionNetwork(object):
         for r, (k, reac, prod, sf) in enumerate(self.reactions):
             c[r] = sf * p[self._pp(k)]
         sv = np.zeros(2 * T["nrp"] + 2)
-        sd = np.zeros(4 * T["nrp"] + 2)
+        sd = np.zeros(4 * T["nrp"] + 2 + gl)
         for r in range(T["nrp"]):
             a, b = T["rtab"][r] & 0xffff, T["rtab"][r] >> 16
             cy = c[r] * yi[b]
@@ -269,17 +289,23 @@ class MassActionNetwork(object):
             sd[4 * r:4 * r + 4] = [da, -da, db, -db]
         f = np.zeros(ns)
         J = np.zeros((ns, ns))
-        for slot, (width, ef, ftab, ej, jtab, base) in enumerate(((gl, T["ef"], T["ftab"], T["ej"], T["jtab"], 0),
-                                                               (nxa, T["ef2"], T["ftab2"], T["ej2"], T["jtab2"], nc))):
+        for width, ef, ftab, base in ((gl, T["ef"], T["ftab"], 0), (nxa, T["ef2"], T["ftab2"], nc)):
             for lane in range(width):
-                if base + lane >= ns or (slot == 0 and lane >= nc):
+                if base + lane >= ns or (base == 0 and lane >= nc):
                     continue
                 f[base + lane] = sum(sv[ftab[e * width + lane]] for e in range(ef))
-                acc = 0.0
-                for e in range(ej):
-                    w = jtab[e * width + lane]
-                    acc = sd[w & 0xffff] + (0.0 if w >> 24 else acc)
-                    J[base + lane, (w >> 16) & 0xff] = acc
+        for lane in range(min(nxa, ns - nc)):                  # leaf rows, stored as rows
+            acc = 0.0
+            for e in range(T["ej2"]):
+                w = T["jtab2"][e * nxa + lane]
+                acc = sd[w & 0xffff] + (0.0 if w >> 24 else acc)
+                J[nc + lane, (w >> 16) & 0xff] = acc
+        diag = 0.0                                              # the device adds 1/(gamma h) here
+        for lane in range(gl):                                  # every lane's own diagonal slot
+            sd[T["dg"] + lane] = diag + sum(sd[T["dtab"][e * gl + lane]] for e in range(T["ed"]))
+        for q, (off, depth) in enumerate(T["mcols"]):           # the register row, column by column: M = -J
+            for lane in range(nc):
+                J[lane, q] = -sum(sd[T["mtab"][(off + e) * gl + lane]] for e in range(depth))
         perm = np.array(pl.perm)
         fo = np.zeros(ns)
         fo[perm] = f
@@ -324,8 +350,8 @@ class MassActionNetwork(object):
                 ("double", "init_val", init_val), ("int", "init_par", init_par), ("int", "obs_ptr", obs_ptr),
                 ("int", "obs_sp", obs_sp), ("double", "obs_coef", obs_coef),
                 ("unsigned int", "rtab", T["rtab"]), ("unsigned short", "ftab", T["ftab"]),
-                ("unsigned short", "ftab2", T["ftab2"]), ("unsigned int", "jtab", T["jtab"]),
-                ("unsigned int", "jtab2", T["jtab2"]))
+                ("unsigned short", "ftab2", T["ftab2"]), ("unsigned short", "dtab", T["dtab"]),
+                ("unsigned short", "mtab", T["mtab"]), ("unsigned int", "jtab2", T["jtab2"]))
         tables = [arr(t, n, v) for t, n, v in spec]
         acc = ["    static __device__ __forceinline__ %s %s(int i) { return T_%s[i]; }" % (t, n, n) for t, n, v in spec]
         struct = ["// species, internal order: " + " ".join(order),
@@ -333,11 +359,23 @@ class MassActionNetwork(object):
                   "    static constexpr int NS = %d, NC = %d, NX = %d, NXA = %d, NP = %d, NR = %d, NOBS = %d, GL = %d, "
                   "LD = %d;" % (ns, pl.nc, pl.nx, T["nxa"], self.np_, len(self.reactions), len(self.obs_names), pl.gl,
                                 T["ld"]),
-                  "    static constexpr int NRM = %d, NRP = %d, EF = %d, EF2 = %d, EJ = %d, EJ2 = %d, XS = %d;"
-                  % (T["nrm"], T["nrp"], T["ef"], T["ef2"], T["ej"], T["ej2"], pl.xs_stride())]
+                  "    static constexpr int NRM = %d, NRP = %d, EF = %d, EF2 = %d, ED = %d, EM = %d, EJ2 = %d, XS = %d;"
+                  % (T["nrm"], T["nrp"], T["ef"], T["ef2"], T["ed"], len(T["mtab"]) // pl.gl, T["ej2"], pl.xs_stride())]
         struct += acc
+        lm = []
+        for q, (off, depth) in enumerate(T["mcols"]):
+            dst = "M[%d]" % q if q < pl.nc else "A[%d]" % (q - pl.nc)
+            terms = ["sd[mt[%d * GL + lane]]" % (off + e) for e in range(depth)]
+            lm.append("        %s = %s;" % (dst, " + ".join(terms) if terms else "0.0"))
+        for l in range(pl.nx, T["nxa"]):
+            lm.append("        A[%d] = 0.0;" % l)
+        struct += ["    // this lane's row of M = diag*I - J and its entries A in the leaf columns, gathered column by column",
+                   "    // from the signed derivative table sd (mt = the column index lists in shared memory)",
+                   "    static __device__ __forceinline__ void load_m(double (&M)[NC], double (&A)[NXA], const double *sd, "
+                   "const unsigned short *mt, int lane) {",
+                   "\n".join(lm), "    }"]
         struct += ["    // M = diag*I - J factored in place: lane i holds core row i (L below the diagonal, U on and",
-                   "    // above it), A the lane's multipliers of the leaf columns; J = Jacobian rows in shared memory",
+                   "    // above it), A the lane's multipliers of the leaf columns; J = the LEAF rows of the Jacobian in shared memory",
                    "    static __device__ __forceinline__ bool lu(double (&M)[NC], double (&A)[NXA], const double *J, "
                    "double diag, int lane,",
                    "                                              unsigned gmask, int gbase, double &inv_d, double &inv_d2) {",

@@ -235,27 +235,26 @@ class CoopPlan(object):
     # ---- CUDA emission ---------------------------------------------------------------------------------
     def cuda_lu(self):
         """Body of Net::lu: factor in place.  Registers: M[NC] (this lane's core row), A[NXA] (its
-        entries in the leaf columns); J = the group's Jacobian rows in shared memory (leaf rows are
-        read from there); inv_d receives 1/U_ii of the lane's own row; returns the lane's verdict on
+        entries in the leaf columns); J = the LEAF rows of the Jacobian in shared memory (row l = leaf l); inv_d receives 1/U_ii of the lane's own row; returns the lane's verdict on
         the pivots.  Branch-free: a lane at or above the pivot row takes part with a zero multiplier."""
         nc, nx = self.nc, self.nx
         out = ["        bool ok = true;"]
         for l in range(nx):
             e = nc + l
             out.append("        {   // leaf %d (internal species %d)" % (l, e))
-            out.append("            const double de = diag - J[%d * LD + %d];" % (e, e))
+            out.append("            const double de = diag - J[%d * LD + %d];" % (l, e))
             out.append("            ok = ok & (fabs(de) > 1e-300);")
-            out.append("            const double ie = 1.0 / de;")
+            out.append("            const double ie = gl::rcp_newton(de);")
             out.append("            A[%d] *= ie;" % l)
             for q in self.leaf_rows[l]:
-                out.append("            M[%d] = fma(A[%d], J[%d * LD + %d], M[%d]);" % (q, l, e, q, q))
+                out.append("            M[%d] = fma(A[%d], J[%d * LD + %d], M[%d]);" % (q, l, l, q, q))
             out.append("            inv_d2 = lane == %d ? ie : inv_d2;" % l)
             out.append("        }")
         for c, cols in self.lu_ops:
             out.append("        {   // pivot %d" % c)
             out.append("            const double piv = gl::shfl_f64(gmask, M[%d], gbase + %d);" % (c, c))
             out.append("            ok = ok & (fabs(piv) > 1e-300);")
-            out.append("            const double ip = 1.0 / piv;")
+            out.append("            const double ip = gl::rcp_newton(piv);")
             out.append("            inv_d = lane == %d ? ip : inv_d;" % c)
             if cols or any(c in lv for lv in self.fwd_levels):
                 out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
@@ -328,7 +327,7 @@ class CoopPlan(object):
                 e = nc + l
                 out.append("            if (lane == %d) {" % l)
                 for q in self.leaf_rows[l]:
-                    out.append("                b2 = fma(J[%d * LD + %d], X[%d], b2);" % (e, q, q))
+                    out.append("                b2 = fma(J[%d * LD + %d], X[%d], b2);" % (l, q, q))
                 out.append("                b2 *= inv_d2;")
                 out.append("            }")
             out.append("        }")
