@@ -140,7 +140,7 @@ struct CoopCounters {
 //   load_m(M, A, sd, mtab, lane)
 //   init_kind(i) (0 const, 1 parameter), init_val(i) (double), init_par(i)
 //   obs_ptr(o), obs_sp(z), obs_coef(z) (double)
-//   lu(M, A, J, diag, lane, gmask, gbase, inv_d2) -> pivots ok;  solve(M, A, J, inv_d, inv_d2, b, b2, ...)
+//   lu(M, A, J, diag, lane, gmask, gbase, inv_d, inv_d2, xs) -> pivots ok;  solve(M, A, J, inv_d, inv_d2, b, b2, ...)
 template <class Net>
 struct CoopOde {
     static constexpr int NS = Net::NS, NC = Net::NC, NX = Net::NX, NXA = Net::NXA, GL = Net::GL, NR = Net::NR;
@@ -277,7 +277,7 @@ struct CoopOde {
         Net::load_m(M, A, sh.sd, T.mtab, lane);
         __syncwarp(gmask);                               // sd is reused by the substitutions
         double inv_d = 1.0, inv_d2 = 0.0;
-        const bool ok = Net::lu(M, A, sh.J, diag, lane, GL == 32 ? 0xffffffffu : gmask, gbase, inv_d, inv_d2);
+        const bool ok = Net::lu(M, A, sh.J, diag, lane, GL == 32 ? 0xffffffffu : gmask, gbase, inv_d, inv_d2, sh.sd);
         if (!__all_sync(gmask, ok)) return false;
         const unsigned gtm = (1u << lane) - 1u;          // bit c set: lane > c
         const unsigned ltm = ~((2u << lane) - 1u);       // bit c set: lane < c

@@ -378,7 +378,8 @@ class MassActionNetwork(object):
                    "    // above it), A the lane's multipliers of the leaf columns; J = the LEAF rows of the Jacobian in shared memory",
                    "    static __device__ __forceinline__ bool lu(double (&M)[NC], double (&A)[NXA], const double *J, "
                    "double diag, int lane,",
-                   "                                              unsigned gmask, int gbase, double &inv_d, double &inv_d2) {",
+                   "                                              unsigned gmask, int gbase, double &inv_d, double &inv_d2, "
+                   "double *xs) {",
                    pl.cuda_lu(), "    }",
                    "    // U -> D^-1 U; ltm = bit mask of the lanes above this one",
                    "    static __device__ __forceinline__ void scale_u(double (&M)[NC], double inv_d, unsigned ltm) {",

@@ -252,15 +252,36 @@ class CoopPlan(object):
             out.append("        }")
         for c, cols in self.lu_ops:
             out.append("        {   // pivot %d" % c)
-            out.append("            const double piv = gl::shfl_f64(gmask, M[%d], gbase + %d);" % (c, c))
+            used = bool(cols or any(c in lv for lv in self.fwd_levels))
+            if self.LU_BROADCAST == "smem":
+                # the pivot lane publishes its pivot and the structural nonzeros of its row (128-bit stores), all
+                # lanes read them back as broadcasts: ~k + 2 instructions per pivot where 64-bit shuffles cost
+                # 2 SHFL + the moves that re-pair the halves per value.  Two buffers alternate, one sync per pivot.
+                vals = ["M[%d]" % c] + ["M[%d]" % q for q in cols]
+                if len(vals) & 1:
+                    vals.append("0.0")
+                out.append("            double2 *X = reinterpret_cast<double2 *>(xs + %d);" % ((c & 1) * self.lu_buf_stride()))
+                out.append("            if (lane == %d) {" % c)
+                for j in range(0, len(vals), 2):
+                    out.append("                X[%d] = make_double2(%s, %s);" % (j // 2, vals[j], vals[j + 1]))
+                out.append("            }")
+                out.append("            __syncwarp(gmask);")
+                for j in range(0, len(vals), 2):
+                    out.append("            const double2 r%d = X[%d];" % (j // 2, j // 2))
+                bc = lambda z: "r%d.%s" % (z // 2, "xy"[z & 1])
+                out.append("            const double piv = %s;" % bc(0))
+            else:
+                bc = None
+                out.append("            const double piv = gl::shfl_f64(gmask, M[%d], gbase + %d);" % (c, c))
             out.append("            ok = ok & (fabs(piv) > 1e-300);")
             out.append("            const double ip = gl::rcp_newton(piv);")
             out.append("            inv_d = lane == %d ? ip : inv_d;" % c)
-            if cols or any(c in lv for lv in self.fwd_levels):
+            if used:
                 out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
                 out.append("            M[%d] = lane > %d ? lz : M[%d];" % (c, c, c))
-                for q in cols:
-                    out.append("            M[%d] = fma(-lz, gl::shfl_f64(gmask, M[%d], gbase + %d), M[%d]);" % (q, q, c, q))
+                for z, q in enumerate(cols):
+                    src = bc(z + 1) if bc else "gl::shfl_f64(gmask, M[%d], gbase + %d)" % (q, c)
+                    out.append("            M[%d] = fma(-lz, %s, M[%d]);" % (q, src, q))
             out.append("        }")
         out.append("        return ok;")
         return "\n".join(out)
@@ -269,9 +290,22 @@ class CoopPlan(object):
     # network (tools/jarm_check.py, steps/s): 0 -> 7.23e7, 2 -> 7.20e7, 4 -> 7.16e7, 32 (all shuffles) -> 6.23e7.
     SHUFFLE_LEVEL_WIDTH = int(__import__("os").environ.get("GLEIPNIR_SHFL_WIDTH", "0"))
 
+    # how the elimination broadcasts a pivot row: "shfl" (64-bit shuffles) or "smem" (pivot lane stores, all load).
+    # Measured on the JARM network (tools/jarm_check.py, 40 000 prior draws, ODE steps/s): shfl 9.2e7, smem 9.4e7;
+    # substitution columns: select 9.4e7, mask_t 9.2e7.
+    LU_BROADCAST = __import__("os").environ.get("GLEIPNIR_LU_BROADCAST", "smem")
+    # how a substitution column is masked: "select" (FMA, then select the result) or "mask_t" (zero the broadcast
+    # value on the lanes that do not take part: the selects leave the dependent chain of b)
+    SOLVE_FORM = __import__("os").environ.get("GLEIPNIR_SOLVE_FORM", "select")
+
+    def lu_buf_stride(self):
+        """Doubles per broadcast buffer of the elimination (pivot + longest pivot row, padded to a pair)."""
+        m = max([len(cols) + 1 for _, cols in self.lu_ops] + [2])
+        return m + (m & 1)
+
     def xs_stride(self):
         """Doubles per broadcast buffer of the substitution: one slot per lane plus one per leaf."""
-        return max(self.gl, self.nc) + max(self.nx, 0)
+        return max(max(self.gl, self.nc) + max(self.nx, 0), self.lu_buf_stride())
 
     def cuda_scale_u(self):
         """After the factorisation: U -> D^-1 U (unit upper triangular), so that the backward substitution needs
@@ -310,7 +344,10 @@ class CoopPlan(object):
                 for c in cols:
                     out.append("            const double t%d = X[%d];" % (c, c))
             for c in cols:
-                out.append("            if (%s & %du) b = fma(-M[%d], t%d, b);" % (mask, 1 << c, c, c))
+                if self.SOLVE_FORM == "mask_t":
+                    out.append("            b = fma(-M[%d], (%s & %du) ? t%d : 0.0, b);" % (c, mask, 1 << c, c))
+                else:
+                    out.append("            if (%s & %du) b = fma(-M[%d], t%d, b);" % (mask, 1 << c, c, c))
             out.append("        }")
         for level in self.fwd_levels:
             level_code(level, "gtm")
