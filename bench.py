@@ -408,9 +408,13 @@ def run_c5(args, env):
     launches_per_step = w["tuning_cycles"] + 1 + 1          # walker phases + the kill / fused sharded step
     # per-kernel time for the roofline: events around every walker launch, in 2 extra steps
     eng.profile_enable(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
     for i in range(n_steps, n_steps + n_prof):
         advance((i + 2) * k, (i + 1) * k)
+    p1.record()
     torch.cuda.synchronize()
+    prof_ms = p0.elapsed_time(p1)
     walk_ms, walk_launches, sel_ms, sel_launches = eng.profile_read()
     ctr_prof = like.counters(reset=True)
     eng.profile_enable(False)
@@ -420,7 +424,7 @@ def run_c5(args, env):
     return dict(like=like, eng=eng, k=k, N=N, t_dev=t_dev, evals=evals, solves=solves, ode_steps=steps_ode,
                 nominal_evals=nominal_evals, clocks=clk, t_init=t_init, launches=args.steps * launches_per_step * world,
                 walk_ms=walk_ms, walk_launches=walk_launches, sel_ms=sel_ms, sel_launches=sel_launches,
-                ctr_prof=ctr_prof, state=st, ms_steps=times, n_prof=n_prof)
+                ctr_prof=ctr_prof, state=st, ms_steps=times, n_prof=n_prof, prof_ms=prof_ms)
 
 
 def run_c5_e2e(args, env, k):
@@ -665,7 +669,7 @@ def run_b200_arm(args):
                     solves_per_eval=c5["solves"] / max(c5["evals"], 1),
                     rhs_evals_per_s=6.0 * steps_prof / walk_s if walk_s > 0 else None,
                     avg_launch_ms=c5["walk_ms"] / max(c5["walk_launches"], 1), launches_timed=int(c5["walk_launches"]),
-                    walker_share_of_step=c5["walk_ms"] / c5["n_prof"] / step_ms,
+                    walker_share_of_step=c5["walk_ms"] / c5["prof_ms"],
                     select_avg_launch_us=1e3 * c5["sel_ms"] / max(c5["sel_launches"], 1),
                     timing="CUDA events around the walker launches of %d extra step(s) after the timed region" % c5["n_prof"],
                     note="latency-bound: a walker is a chain of 721 dependent likelihood evaluations, each 2 x (pre-equilibration "

@@ -36,7 +36,7 @@ __global__ void dense_gaussian_pack_kernel(const double *__restrict__ P, int d, 
 // pairs are in flight (a dependent chain of KT DMMAs per pair was the r1 limiter: 27 % of the DMMA peak) and every
 // B fragment fetched from shared memory feeds two DMMAs.
 template <int KTM>
-__global__ void __launch_bounds__(DG_WARPS * 32) dense_gaussian_dmma_kernel(
+__global__ void __launch_bounds__(DG_WARPS * 32, 2) dense_gaussian_dmma_kernel(
     const double *__restrict__ x, long long n, int d, int KT, int NT, const double *__restrict__ mu,
     const double *__restrict__ Pf, double log_norm, double *__restrict__ out) {
     extern __shared__ double sm[];
@@ -53,11 +53,22 @@ __global__ void __launch_bounds__(DG_WARPS * 32) dense_gaussian_dmma_kernel(
         const long long r0 = t * 16;
         const int rows = (int)((n - r0) < 16 ? (n - r0) : 16);
         // stage the residual tiles (coalesced: rows*d contiguous doubles), zero padding
-        for (int c = lane; c < dp; c += 32) {                   // lane = column: no index division, rows coalesced
+        // (lane = column: no index division, rows coalesced).  All 16 row loads of a column pass are issued before
+        // the first store: the staging phase is one memory latency per pass instead of four (it was as long as the
+        // DMMA phase of the tile).
+        for (int c = lane; c < dp; c += 32) {
             const double m = c < d ? __ldg(mu + c) : 0.0;
-#pragma unroll 4
-            for (int r = 0; r < 16; ++r)
-                Rs[r * dp + c] = (r < rows && c < d) ? x[(r0 + r) * d + c] - m : 0.0;
+            double v[16];
+            const double *src = x + r0 * d + c;
+            if (rows == 16 && c < d) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = __ldg(src + (size_t)r * d);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = (r < rows && c < d) ? __ldg(src + (size_t)r * d) : m;
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) Rs[r * dp + c] = v[r] - m;
         }
         __syncwarp();
         double a0[KTM], a1[KTM];

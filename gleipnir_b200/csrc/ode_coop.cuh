@@ -123,7 +123,21 @@ __device__ __forceinline__ double pmul_mask(int lane, unsigned mask, double b, d
 struct CoopCounters {
     unsigned long long evals, solves, steps;
     unsigned long long next;          // work-claim cursor of the batch-evaluation kernel (zeroed before a launch)
+    // optional trace of the walker launches (gl_plugin_trace): one record per block
+    unsigned long long trace_on, trace_n;
+    unsigned long long trace[4 * 4096];   // (launch phase << 32 | SM id, start ns, end ns, ODE steps of the block)
 };
+constexpr unsigned long long COOP_TRACE_CAP = 4096;
+__device__ __forceinline__ unsigned long long coop_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int coop_smid() {
+    unsigned int s;
+    asm("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
 
 // Net (generated): NS, NC (core rows), NX (leaves), NXA = max(NX,1), NP, NR, NOBS, GL, LD (row stride of the leaf
 // rows of J), NRM = ceil(NR/GL), NRP = NRM*GL, EF/EF2/ED/EM/EJ2 (list depths);
@@ -644,6 +658,8 @@ __global__ void __launch_bounds__(128, GL_COOP_MIN_BLOCKS) walk_coop_kernel(Walk
     typename C::Shared &sh = shs[g];
     C::init_shared(sh, lane, gmask);
     unsigned long long evals = 0ull;
+    const bool tracing = ctr->trace_on != 0ull;
+    const unsigned long long t_begin = tracing ? coop_globaltimer() : 0ull;
     double *x = xs + wl;
     const double lstar = S->lstar;
     const uint32_t step = (uint32_t)S->step;
@@ -726,6 +742,21 @@ __global__ void __launch_bounds__(128, GL_COOP_MIN_BLOCKS) walk_coop_kernel(Walk
         for (int j = tid; j < d; j += 128)
             if (acc[j]) atomicAdd(&S->acc[phase][j], acc[j]);
     }
+    if (tracing) {
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long steps = 0ull;
+            for (int q = 0; q < GPB; ++q) steps += shs[q].n_steps;
+            const unsigned long long slot = atomicAdd(&ctr->trace_n, 1ull);
+            if (slot < COOP_TRACE_CAP) {
+                unsigned long long *r = ctr->trace + 4 * slot;
+                r[0] = ((unsigned long long)phase << 32) | coop_smid();
+                r[1] = t_begin;
+                r[2] = coop_globaltimer();
+                r[3] = steps;
+            }
+        }
+    }
 }
 
 // groups a walker spreads its conditions over: as many as there are conditions while a block still
@@ -774,12 +805,31 @@ inline int ode_coop_eval_launch(const ModelDev &M, const double *x, long long n,
     return GL_OK;
 }
 
+// switch the walker trace on/off (clears it), or read it: returns the number of records copied to out (4 words each)
+template <class Net>
+inline long long coop_trace(int enable, unsigned long long *out, long long max_records) {
+    CoopCounters *ctr = coop_counter_store<Net>();
+    if (!ctr) return -1;
+    if (out == nullptr) {
+        unsigned long long v[2] = {enable ? 1ull : 0ull, 0ull};
+        if (cudaMemcpy(&ctr->trace_on, v, sizeof(v), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+        return 0;
+    }
+    unsigned long long n = 0;
+    if (cudaMemcpy(&n, &ctr->trace_n, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (n > COOP_TRACE_CAP) n = COOP_TRACE_CAP;
+    if ((long long)n > max_records) n = (unsigned long long)max_records;
+    if (n && cudaMemcpy(out, ctr->trace, 4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)n;
+}
+
 template <class Net>
 inline int coop_counters(unsigned long long *out3, int reset) {
-    CoopCounters h, *ctr = coop_counter_store<Net>();
+    CoopCounters *ctr = coop_counter_store<Net>();
     GL_REQUIRE(ctr != nullptr, "counter allocation failed");
-    GL_CUDA(cudaMemcpy(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost));
-    out3[0] = h.evals; out3[1] = h.solves; out3[2] = h.steps;
+    unsigned long long h3[3];
+    GL_CUDA(cudaMemcpy(h3, ctr, sizeof(h3), cudaMemcpyDeviceToHost));
+    out3[0] = h3[0]; out3[1] = h3[1]; out3[2] = h3[2];
     if (reset) GL_CUDA(cudaMemset(ctr, 0, 3 * sizeof(unsigned long long)));
     return GL_OK;
 }

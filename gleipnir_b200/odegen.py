@@ -452,6 +452,9 @@ GL_API void gl_plugin_info(int *ns, int *np, int *nobs) {
     *ns = Net::NS; *np = Net::NP; *nobs = Net::NOBS;
 }
 GL_API int gl_plugin_counters(unsigned long long *out3, int reset) { return gl::coop_counters<Net>(out3, reset); }
+GL_API long long gl_plugin_trace(int enable, unsigned long long *out, long long max_records) {
+    return gl::coop_trace<Net>(enable, out, max_records);
+}
 }
 '''
 
@@ -642,6 +645,24 @@ class OdeNetworkLogLikelihood(DeviceLogLikelihood):
         out = (ctypes.c_ulonglong * 3)()
         _lib.check(self._plugin.gl_plugin_counters(out, 1 if reset else 0))
         return dict(evals=int(out[0]), solves=int(out[1]), steps=int(out[2]))
+
+    def trace(self, enable=None):
+        """Walker-launch trace of the cooperative solver (diagnostics): ``trace(True)`` / ``trace(False)`` switch it on
+        (clearing it) / off; ``trace()`` returns an int64 array [n, 4] of (phase << 32 | SM id, start ns, end ns, ODE
+        steps) per walker block since it was switched on."""
+        self.device_model()
+        fn = self._plugin.gl_plugin_trace
+        fn.restype = ctypes.c_longlong
+        fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
+        if enable is not None:
+            if fn(1 if enable else 0, None, 0) < 0:
+                raise RuntimeError("trace switch failed")
+            return None
+        buf = np.zeros((4096, 4), dtype=np.uint64)
+        n = fn(0, buf.ctypes.data, 4096)
+        if n < 0:
+            raise RuntimeError("trace read failed")
+        return buf[:n].astype(np.int64)
 
 
 class OdeProtocolLogLikelihood(OdeNetworkLogLikelihood):

@@ -277,11 +277,15 @@ class CoopPlan(object):
             out.append("            const double ip = gl::rcp_newton(piv);")
             out.append("            inv_d = lane == %d ? ip : inv_d;" % c)
             if used:
-                out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
-                out.append("            M[%d] = lane > %d ? lz : M[%d];" % (c, c, c))
+                if self.NEG_FACTORS:
+                    out.append("            const double nlz = lane > %d ? -(M[%d] * ip) : 0.0;" % (c, c))
+                    out.append("            M[%d] = lane > %d ? nlz : M[%d];" % (c, c, c))
+                else:
+                    out.append("            const double lz = lane > %d ? M[%d] * ip : 0.0;" % (c, c))
+                    out.append("            M[%d] = lane > %d ? lz : M[%d];" % (c, c, c))
                 for z, q in enumerate(cols):
                     src = bc(z + 1) if bc else "gl::shfl_f64(gmask, M[%d], gbase + %d)" % (q, c)
-                    out.append("            M[%d] = fma(-lz, %s, M[%d]);" % (q, src, q))
+                    out.append("            M[%d] = fma(%s, %s, M[%d]);" % (q, "nlz" if self.NEG_FACTORS else "-lz", src, q))
             out.append("        }")
         out.append("        return ok;")
         return "\n".join(out)
@@ -298,6 +302,10 @@ class CoopPlan(object):
     # value on the lanes that do not take part: the selects leave the dependent chain of b)
     SOLVE_FORM = __import__("os").environ.get("GLEIPNIR_SOLVE_FORM", "select")
 
+    # the factors are kept NEGATED in the register row (-L below the diagonal, -D^-1 U above it): the substitution
+    # FMAs then need no negated operand
+    NEG_FACTORS = __import__("os").environ.get("GLEIPNIR_NEG_FACTORS", "0") == "1"
+
     def lu_buf_stride(self):
         """Doubles per broadcast buffer of the elimination (pivot + longest pivot row, padded to a pair)."""
         m = max([len(cols) + 1 for _, cols in self.lu_ops] + [2])
@@ -310,7 +318,10 @@ class CoopPlan(object):
     def cuda_scale_u(self):
         """After the factorisation: U -> D^-1 U (unit upper triangular), so that the backward substitution needs
         one unconditional scaling of the right-hand side instead of a predicated one per level."""
-        return "\n".join("        if (ltm & %du) M[%d] *= inv_d;" % (1 << q if q < 32 else 0, q) for q in range(1, self.nc))
+        f = "ninv_d" if self.NEG_FACTORS else "inv_d"
+        head = ["        const double ninv_d = -inv_d;"] if self.NEG_FACTORS else []
+        return "\n".join(head + ["        if (ltm & %du) M[%d] *= %s;" % (1 << q if q < 32 else 0, q, f)
+                                 for q in range(1, self.nc)])
 
     def cuda_solve(self):
         """Body of Net::solve: b (core entry of this lane), b2 (leaf entry of lanes < NX).
@@ -344,10 +355,11 @@ class CoopPlan(object):
                 for c in cols:
                     out.append("            const double t%d = X[%d];" % (c, c))
             for c in cols:
+                m = "M[%d]" % c if self.NEG_FACTORS else "-M[%d]" % c
                 if self.SOLVE_FORM == "mask_t":
-                    out.append("            b = fma(-M[%d], (%s & %du) ? t%d : 0.0, b);" % (c, mask, 1 << c, c))
+                    out.append("            b = fma(%s, (%s & %du) ? t%d : 0.0, b);" % (m, mask, 1 << c, c))
                 else:
-                    out.append("            if (%s & %du) b = fma(-M[%d], t%d, b);" % (mask, 1 << c, c, c))
+                    out.append("            if (%s & %du) b = fma(%s, t%d, b);" % (mask, 1 << c, m, c))
             out.append("        }")
         for level in self.fwd_levels:
             level_code(level, "gtm")

@@ -203,7 +203,7 @@ def test_cooperative_plugin_exports_counters():
     so = odegen.compile_plugin(networks.jarm())
     out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
     for sym in ("gl_plugin_walk_launch", "gl_plugin_eval_launch", "gl_plugin_last_error", "gl_plugin_info",
-                "gl_plugin_counters"):
+                "gl_plugin_counters", "gl_plugin_trace"):
         assert re.search(r" T %s\b" % sym, out), sym
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
