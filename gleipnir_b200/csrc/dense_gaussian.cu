@@ -7,6 +7,8 @@
 // shared memory, loaded once per CTA), and the row dot q_i = sum_j R_ij Y_ij is folded into the
 // accumulator read-out, so Y never leaves registers.
 // Algorithmic work: 2d^2 + 2d flop and 8d + 8 B per point (12.5 flop/B at d = 50).
+#include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 #include "likelihoods.cuh"
 
@@ -122,10 +124,146 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 2) dense_gaussian_dmma_kernel(
     }
 }
 
+// Round 2, second form: the RAW rows of the next 16-row tile are copied into the warp's second shared-memory
+// buffer with cp.async while the DMMAs of the current tile run, so the staging phase (one HBM latency per tile,
+// as long as a quarter of the tile's DMMA time) disappears from the warp's critical path.  The tile is kept as
+// the contiguous 16*d doubles it is in HBM (16-byte copies, no padding); mu is subtracted when the A fragments
+// and the epilogue operands are read, and the padding columns (k >= d, n >= d) are masked there.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NTM>
+__global__ void __launch_bounds__(DG_WARPS * 32, 2) dense_gaussian_dmma_pipe_kernel(
+    const double *__restrict__ x, long long n, int d, int KT, const double *__restrict__ mu,
+    const double *__restrict__ Pf, double log_norm, double *__restrict__ out) {
+    // k-outer: per k-slice one A fragment per row tile and NTM B fragments feed 2*NTM DMMAs on 2*NTM INDEPENDENT
+    // accumulator pairs (the n-outer form above has four chains of KT dependent DMMAs per warp)
+    constexpr int NT = NTM;
+    extern __shared__ double sm[];
+    const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;
+    const int tile_len = 16 * d;                               // doubles per raw tile (even: 16-byte copies)
+    double *Ps = sm;                                           // [KT*NT*32]
+    double *mus = Ps + (size_t)KT * NT * 32;                   // [dp + 16] mu, zero padded
+    double *Xs_all = mus + dp + 16;                            // [warps][2][tile_len]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int e = tid; e < KT * NT * 32; e += blockDim.x) Ps[e] = Pf[e];
+    for (int e = tid; e < dp + 16; e += blockDim.x) mus[e] = e < d ? mu[e] : 0.0;
+    __syncthreads();
+    double *Xw = Xs_all + (size_t)warp * 2 * tile_len;
+    const int grp = lane >> 2, tig = lane & 3;
+    const long long n_tiles = (n + 15) / 16;
+    const long long stride = (long long)gridDim.x * nw;
+    long long t = (long long)blockIdx.x * nw + warp;
+    auto fetch = [&](long long tile, double *dst) {            // rows [16 tile, 16 tile + 16) clipped to n
+        const long long r0 = tile * 16;
+        const int len = (int)((n - r0 < 16 ? n - r0 : 16) * d);    // doubles
+        const double *src = x + r0 * d;
+        for (int e = lane * 2; e + 1 < len; e += 64) cp_async16(dst + e, src + e);
+        if ((len & 1) && lane == 0) dst[len - 1] = src[len - 1];    // odd tail (last partial tile, odd d)
+    };
+    int buf = 0;
+    if (t < n_tiles) fetch(t, Xw);
+    cp_async_commit();
+    for (; t < n_tiles; t += stride) {
+        const long long tn = t + stride;
+        if (tn < n_tiles) fetch(tn, Xw + (buf ^ 1) * tile_len);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const double *Rs = Xw + buf * tile_len;
+        const long long r0 = t * 16;
+        const int rows = (int)((n - r0) < 16 ? (n - r0) : 16);
+        const bool ok0 = grp < rows, ok1 = 8 + grp < rows;
+        const double *row0 = Rs + grp * d, *row1 = Rs + (8 + grp) * d;
+        double c0[NT], e0[NT], c1[NT], e1[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) c0[nt] = e0[nt] = c1[nt] = e1[nt] = 0.0;
+        const double *B = Ps + lane;
+        // (a hand-made software pipeline over the k-slices -- fragments of slice ks+1 requested before the DMMAs of
+        // slice ks -- measured slower: 18.9 vs 19.7 TFLOP/s at d = 50; the loads are not what the DMMAs wait for)
+#pragma unroll 2
+        for (int ks = 0; ks < KT; ++ks) {
+            const int c = ks * 4 + tig;
+            const bool in = c < d;
+            const double m_ = mus[c];                          // zero beyond d
+            const double a0 = (in && ok0) ? row0[c] - m_ : 0.0;
+            const double a1 = (in && ok1) ? row1[c] - m_ : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b = B[(ks * NT + nt) * 32];
+                dmma_m8n8k4(c0[nt], e0[nt], a0, b);
+                dmma_m8n8k4(c1[nt], e1[nt], a1, b);
+            }
+        }
+        // accumulator layout: row = grp, cols = nt*8 + tig*2 + {0,1}
+        double q0a = 0.0, q0b = 0.0, q1a = 0.0, q1b = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = nt * 8 + tig * 2;
+            const bool i0 = col < d, i1 = col + 1 < d;
+            const double m0 = mus[col], m1 = mus[col + 1];
+            q0a = fma(c0[nt], (ok0 && i0) ? row0[col] - m0 : 0.0, q0a);
+            q0b = fma(e0[nt], (ok0 && i1) ? row0[col + 1] - m1 : 0.0, q0b);
+            q1a = fma(c1[nt], (ok1 && i0) ? row1[col] - m0 : 0.0, q1a);
+            q1b = fma(e1[nt], (ok1 && i1) ? row1[col + 1] - m1 : 0.0, q1b);
+        }
+        double q0 = q0a + q0b, q1 = q1a + q1b;
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        if (tig == 0 && ok0) out[r0 + grp] = -0.5 * q0 + log_norm;
+        if (tig == 0 && ok1) out[r0 + 8 + grp] = -0.5 * q1 + log_norm;
+        __syncwarp();                                          // everybody is done with this buffer
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
 int dense_gaussian_eval_launch(const gl_model *m, const double *x, long long n, double *out, cudaStream_t st) {
     const int d = m->dev.d;
     const int KT = (d + 3) / 4, NT = (d + 7) / 8;
     const int dp = KT * 4 > NT * 8 ? KT * 4 : NT * 8;
+    const size_t p_bytes = sizeof(double) * (size_t)KT * NT * 32;
+    // pipelined form: two raw 16-row tiles per warp; as many warps per block (<= 8) as let two blocks share an SM
+    {
+        const size_t fixed = p_bytes + sizeof(double) * (dp + 16), per_warp = sizeof(double) * 2 * 16 * (size_t)d;
+        int warps = DG_WARPS;
+        while (warps > 2 && fixed + warps * per_warp > 112 * 1024) --warps;
+        const size_t smem = fixed + warps * per_warp;
+        const bool aligned = ((uintptr_t)x & 15) == 0;
+        static const bool off = getenv("GLEIPNIR_DMMA_NO_PIPELINE") != nullptr;
+        if (!off && aligned && smem <= 112 * 1024 && n >= 16 && NT <= 8) {
+            long long blocks = ((n + 15) / 16 + warps - 1) / warps;
+            const long long cap = (long long)sm_count() * 2;
+            if (blocks > cap) blocks = cap;
+#define GL_DG_PIPE(NTM)                                                                                          \
+    do {                                                                                                         \
+        GL_CUDA(cudaFuncSetAttribute(dense_gaussian_dmma_pipe_kernel<NTM>,                                       \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        dense_gaussian_dmma_pipe_kernel<NTM><<<(int)blocks, warps * 32, smem, st>>>(                          \
+            x, n, d, KT, m->dev.aux0, m->dev.aux2, m->dev.s0, out);                                              \
+    } while (0)
+            switch (NT) {
+                case 1: GL_DG_PIPE(1); break;
+                case 2: GL_DG_PIPE(2); break;
+                case 3: GL_DG_PIPE(3); break;
+                case 4: GL_DG_PIPE(4); break;
+                case 5: GL_DG_PIPE(5); break;
+                case 6: GL_DG_PIPE(6); break;
+                case 7: GL_DG_PIPE(7); break;
+                default: GL_DG_PIPE(8); break;
+            }
+#undef GL_DG_PIPE
+            GL_CHECK_LAUNCH();
+            return GL_OK;
+        }
+    }
     int warps = DG_WARPS;                                      // fewer warps per block when P itself fills shared memory
     while (warps > 1 && sizeof(double) * ((size_t)KT * NT * 32 + (size_t)warps * 16 * dp) > 200 * 1024) warps >>= 1;
     const int smem = (int)(sizeof(double) * ((size_t)KT * NT * 32 + (size_t)warps * 16 * dp));
