@@ -173,3 +173,32 @@ def test_reference_jarm_script_flow(cuda):
     again = loglikelihood.evaluate(dp.to_numpy()[fin][-8:, 2:])
     np.testing.assert_allclose(again, ll[fin][-8:], rtol=1e-12)
     assert len(NS.posteriors()) == 18
+
+
+def test_walker_trace_records_every_block(cuda):
+    """The diagnostic trace of the cooperative walker (tools/walker_trace.py): one record per walker block and launch
+    phase, SM ids inside the device, end after start, and the blocks' ODE steps add up to the plugin's counter."""
+    from gleipnir_b200 import _lib as L
+    from gleipnir_b200 import jarm
+    from gleipnir_b200.engine import DeviceEngine
+    like = jarm.jarm_loglikelihood()
+    table = [(L.GL_PRIOR_UNIFORM, a, b) for a, b in jarm.jarm_prior_table()]
+    N, k = 64, 8
+    eng = DeviceEngine(table, like, N, k, 4 * k, iterations=1, burn_in=0, tuning_cycles=1, seed=3)
+    eng.init()
+    eng.kill(k)
+    like.counters(reset=True)
+    like.trace(True)
+    eng.refill()
+    eng.kill(k)
+    tr = like.trace()
+    like.trace(False)
+    c = like.counters(reset=True)
+    n_sm = L.device_info()[0]
+    assert len(tr) == 2 * (k // 2)                      # two walkers per block, tuning + production launch
+    assert set((tr[:, 0] >> 32).tolist()) == {0, 1}
+    assert np.all((tr[:, 0] & 0xffffffff) < n_sm) and np.all(tr[:, 2] >= tr[:, 1])
+    assert int(tr[:, 3].sum()) == c["steps"]
+    like.trace(True)                                     # switching it on again clears it
+    assert len(like.trace()) == 0
+    like.trace(False)

@@ -162,9 +162,11 @@ def test_select_ties_nan_neginf_negzero(cuda):
     assert _select(cuda, x, 1)[0][0] == np.argmin(x) == 7   # np.argmin: first NaN wins
 
 
-@pytest.mark.parametrize("d,n", [(50, 100003), (7, 1001), (8, 8), (128, 4099), (3, 1)])
+@pytest.mark.parametrize("d,n", [(50, 100003), (7, 1001), (8, 8), (128, 4099), (3, 1), (33, 1003), (12, 16), (12, 17),
+                                 (64, 5000), (65, 3001), (1, 40), (50, 15)])
 def test_dense_gaussian_dmma_matches_scalar_kernel_and_oracle(cuda, d, n):
-    """FP64 tensor-core (DMMA) batch kernel vs the scalar DFMA kernel vs numpy, ragged sizes."""
+    """FP64 tensor-core (DMMA) batch kernel vs the scalar DFMA kernel vs numpy, ragged sizes: the cp.async
+    k-outer kernel (d <= 64, n >= 16; odd d, partial last tile), the n-outer kernel beyond, tiny batches."""
     from gleipnir_b200 import _lib as L
     from gleipnir_b200 import likelihoods as lk
     mu, P, ln = olk.make_c3_dense_gaussian(d, seed=d)
@@ -179,6 +181,25 @@ def test_dense_gaussian_dmma_matches_scalar_kernel_and_oracle(cuda, d, n):
     np.testing.assert_allclose(tensor, want, rtol=RTOL, atol=1e-10)
     np.testing.assert_allclose(scalar, want, rtol=RTOL, atol=1e-10)
     np.testing.assert_allclose(tensor, scalar, rtol=RTOL, atol=1e-10)
+
+
+def test_dense_gaussian_dmma_unaligned_rows(cuda):
+    """A batch that starts 8 bytes off a 16-byte boundary takes the kernel without 16-byte async copies."""
+    import torch
+    from gleipnir_b200 import _lib as L
+    from gleipnir_b200 import likelihoods as lk
+    d, n = 33, 515
+    mu, P, ln = olk.make_c3_dense_gaussian(d, seed=3)
+    like = lk.DenseGaussianLogLikelihood(mu, P, ln)
+    x = np.random.default_rng(9).uniform(-5, 5, size=(n, d))
+    flat = torch.empty(n * d + 1, dtype=torch.float64, device="cuda")
+    flat[1:] = torch.as_tensor(x.ravel(), device="cuda")
+    view = flat[1:].view(n, d)                         # data pointer = base + 8
+    assert view.data_ptr() % 16 == 8
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    L.check(L.load().gl_loglike_eval(like.device_model(), view.data_ptr(), n, out.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_allclose(out.cpu().numpy(), olk.dense_gaussian(x, mu, P, ln), rtol=RTOL, atol=1e-10)
 
 
 def test_eggcarton_near_cosine_zeros_and_large_arguments(cuda):
