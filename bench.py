@@ -690,12 +690,13 @@ def run_b200_arm(args):
     steps_prof = c5["ctr_prof"]["steps"]
     achieved = steps_prof * dense_flop / walk_s / 1e12 if walk_s > 0 else None
     step_ms = float(np.mean(c5["ms_steps"]))
-    roofline = dict(kernel="walk_coop_kernel<Net=jarm> (RODAS4, one system per warp, one warp per condition)",
+    roofline = dict(kernel="walk_coop_kernel<Net=jarm> (RODAS4, one system per warp, one warp per condition, 16 warps per SM)",
                     bound="fp64", achieved=achieved, peak=dfma_peak, unit="TFLOP/s",
                     frac=(achieved / dfma_peak) if achieved and dfma_peak else None, traffic=None,
-                    traffic_source="not re-measured in this run; ncu --set full of the same kernel family: "
-                                   "profiles/r02_b_jarm_eval.txt (dram bytes are ~1e-5 of the HBM roof: the state lives in "
-                                   "registers and shared memory)",
+                    traffic_source="not re-measured in this run (bound is fp64, not hbm); ncu --set full of the batch-evaluation "
+                                   "form of the same solver code, profiles/r02_h_jarm_eval_register_gather_4blocks.txt: 3.1 MB of "
+                                   "DRAM traffic in a 62 ms launch = 1e-5 of the HBM roof (the state lives in registers and "
+                                   "shared memory); the walker launch itself: profiles/r02_m_walk_coop_kernel_c5_production_launch.txt",
                     peak_source="gl_microbench_dfma measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     algorithmic_flop_per_ode_step=dense_flop,
                     algorithmic_flop_formula="SURVEY 8d: 4r + 2/3 n^3 + s(3r + 2n^2), n=34 species, r=84 reactions, s=6 stages",
@@ -711,7 +712,7 @@ def run_b200_arm(args):
                     timing="CUDA events around the walker launches of %d extra step(s) after the timed region" % c5["n_prof"],
                     note="latency-bound: a walker is a chain of 721 dependent likelihood evaluations, each 2 x (pre-equilibration "
                          "+ main) stiff solves of ~10^2-10^3 dependent Rosenbrock steps; fp64 pipe utilisation and stall "
-                         "reasons from ncu are in profiles/r02_*")
+                         "reasons from ncu are in profiles/r02_h_* (batch-evaluation form) and profiles/r02_m_* (a real walker launch)")
     cpu = None
     if world == 1 and not args.no_cpu:
         ev, wall = c5_cpu_sample(1, 400)

@@ -11,10 +11,15 @@
 //     memory and are eliminated first (block elimination), so the register matrix stays 32 wide;
 //   * species order, the leaf set, the symbolic LU (with fill) and the level schedules of the
 //     triangular solves are decided ONCE per network by gleipnir_b200/odeplan.py and emitted as
-//     straight-line code (Net::lu, Net::solve): one shuffle + one FMA per structural nonzero of a
-//     pivot row, nothing for structural zeros;
-//   * reaction rates are evaluated by all lanes in parallel into shared memory, then each lane
-//     gathers its own row of f and J (CSR rows of the stoichiometric matrix);
+//     straight-line code (Net::lu, Net::solve): one broadcast + one FMA per structural nonzero of a
+//     pivot row, nothing for structural zeros; pivot rows and substitution vectors are broadcast
+//     through shared memory (128-bit stores by the owning lane, broadcast loads by all);
+//   * reaction rates (and their partial derivatives) are evaluated by all lanes in parallel into signed
+//     value tables in shared memory; each lane then sums its f_i from an index list and gathers its row
+//     of M straight into registers, column by column (Net::load_m) -- no Jacobian rows in shared memory
+//     except those of the leaf species, so a block of four 34-species systems needs 40 KB and four
+//     blocks (16 warps) are resident per SM at 128 registers;
+//   * error control: weighted RMS norm (the reference solver's), step-size factor in single precision;
 //   * no pivoting: M is the identity plus a small multiple of a kinetics Jacobian, the same
 //     assumption KPP-style chemistry solvers make; a vanishing/non-finite pivot fails the step
 //     (the step is retried with h/10).
