@@ -223,3 +223,60 @@ def test_generated_sources_do_not_depend_on_the_hash_seed():
         outs.add(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True, cwd=here,
                                 env=env).stdout.strip())
     assert len(outs) == 1, outs
+
+
+def _random_network(rng, ns, nr, name):
+    """Random uni-/bimolecular mass-action network; duplicate reactant pairs on purpose, so that Jacobian entries
+    off the diagonal get several terms (the shipped networks only have single-term ones)."""
+    from gleipnir_b200.odegen import MassActionNetwork
+    sp = ["S%d" % i for i in range(ns)]
+    par, rx = {}, []
+    pairs = []
+    for r in range(nr):
+        par["k%d" % r] = float(10.0 ** rng.uniform(-2, 1))
+        if pairs and rng.random() < 0.3:
+            reac = list(pairs[rng.integers(len(pairs))])            # same reactants, other products
+        elif rng.random() < 0.5:
+            reac = [sp[rng.integers(ns)]]
+        else:
+            reac = [sp[rng.integers(ns)], sp[rng.integers(ns)]]      # may be a homodimerisation
+        pairs.append(tuple(reac))
+        prod = [sp[i] for i in rng.choice(ns, size=rng.integers(1, 3), replace=False)]
+        rx.append(("k%d" % r, reac, prod))
+    par["S0_0"] = 3.0
+    return MassActionNetwork(name, species=sp, parameters=par, reactions=rx, initials={"S0": "S0_0", "S1": 1.5},
+                             observables={"o": {sp[0]: 1, sp[-1]: 2}})
+
+
+@pytest.mark.parametrize("ns,nr,seed", [(6, 9, 0), (12, 30, 1), (16, 40, 2), (17, 30, 3), (28, 70, 4), (32, 90, 5),
+                                         (33, 60, 6), (35, 70, 7)])
+def test_generated_tables_and_plan_on_random_networks(ns, nr, seed):
+    """coop_tables (column lists of M, diagonal lists, leaf rows) and the elimination plan on random networks:
+    f and J equal the oracle's, (diag*I - J) x = b solved with the plan equals numpy.linalg.solve, and the generated
+    CUDA source mentions every structural column.  Networks above 32 species need independent leaf species; a random
+    network may not have them, which the plan must say loudly."""
+    rng = np.random.default_rng(seed)
+    net = _random_network(rng, ns, nr, "rnd%d" % seed)
+    d = net.description()
+    f, jac = ode.rhs_jac(d)
+    y = rng.uniform(0.05, 2.0, ns)
+    p = d["param_values"] * rng.uniform(0.5, 2.0, net.np_)
+    try:
+        pl = net.plan()
+    except ValueError as exc:
+        assert ns > 32 and "leaf" in str(exc)
+        return
+    fe, Je = net.emulate_rhs_jac(y, p)
+    np.testing.assert_allclose(fe, f(y, 0, p), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(Je, jac(y, 0, p), rtol=1e-12, atol=1e-13)
+    T = net.coop_tables()
+    assert pl.gl == (16 if pl.nc <= 16 else 32) and T["gl"] == pl.gl
+    assert max(dp for _, dp in T["mcols"]) >= 1 and len(T["dtab"]) == T["ed"] * pl.gl
+    J = jac(y, 0, p)
+    diag = 1.0 / (0.25 * 0.05)
+    b = rng.normal(size=ns)
+    x = pl.emulate_solve(J, diag, b)
+    assert x is not None
+    np.testing.assert_allclose(x, np.linalg.solve(diag * np.eye(ns) - J, b), rtol=1e-9, atol=1e-12)
+    src = net.plugin_source()
+    assert "load_m" in src and src.count("M[%d] = " % (pl.nc - 1)) >= 1
