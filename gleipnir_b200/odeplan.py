@@ -250,6 +250,50 @@ class CoopPlan(object):
                 out.append("            M[%d] = fma(A[%d], J[%d * LD + %d], M[%d]);" % (q, l, l, q, q))
             out.append("            inv_d2 = lane == %d ? ie : inv_d2;" % l)
             out.append("        }")
+        if self.LU_BROADCAST == "smem" and self.LU_LEVELS:
+            # pivots that do not couple (no L or U entry between them) form a LEVEL of the elimination DAG: their
+            # lanes publish pivot + row together, ONE sync, then every lane applies them all -- 15 store/sync/load
+            # round trips instead of 32 on the JARM network, and the reciprocals of a level overlap
+            stride = self.lu_level_stride()
+            for li, level in enumerate(self.lu_levels()):
+                out.append("        {   // level %d: pivots %s" % (li, " ".join(str(c) for c in level)))
+                out.append("            double2 *X = reinterpret_cast<double2 *>(xs + %d);" % ((li & 1) * stride))
+                offs, off = {}, 0
+                for c in level:
+                    cols = dict(self.lu_ops)[c]
+                    vals = ["M[%d]" % c] + ["M[%d]" % q for q in cols]
+                    if len(vals) & 1:
+                        vals.append("0.0")
+                    offs[c] = off
+                    out.append("            if (lane == %d) {" % c)
+                    for j in range(0, len(vals), 2):
+                        out.append("                X[%d] = make_double2(%s, %s);" % (off + j // 2, vals[j], vals[j + 1]))
+                    out.append("            }")
+                    off += len(vals) // 2
+                out.append("            __syncwarp(gmask);")
+                for c in level:
+                    cols = dict(self.lu_ops)[c]
+                    nv = len(cols) + 1
+                    for j in range((nv + 1) // 2):
+                        out.append("            const double2 r%d_%d = X[%d];" % (c, j, offs[c] + j))
+                for c in level:
+                    cols = dict(self.lu_ops)[c]
+                    bc = lambda z, c=c: "r%d_%d.%s" % (c, z // 2, "xy"[z & 1])
+                    out.append("            const double piv%d = %s;" % (c, bc(0)))
+                    out.append("            ok = ok & (fabs(piv%d) > 1e-300);" % c)
+                    out.append("            const double ip%d = gl::rcp_newton(piv%d);" % (c, c))
+                    out.append("            inv_d = lane == %d ? ip%d : inv_d;" % (c, c))
+                for c in level:
+                    cols = dict(self.lu_ops)[c]
+                    bc = lambda z, c=c: "r%d_%d.%s" % (c, z // 2, "xy"[z & 1])
+                    if cols or any(c in lv for lv in self.fwd_levels):
+                        out.append("            const double lz%d = lane > %d ? M[%d] * ip%d : 0.0;" % (c, c, c, c))
+                        out.append("            M[%d] = lane > %d ? lz%d : M[%d];" % (c, c, c, c))
+                        for z, q in enumerate(cols):
+                            out.append("            M[%d] = fma(-lz%d, %s, M[%d]);" % (q, c, bc(z + 1), q))
+                out.append("        }")
+            out.append("        return ok;")
+            return "\n".join(out)
         for c, cols in self.lu_ops:
             out.append("        {   // pivot %d" % c)
             used = bool(cols or any(c in lv for lv in self.fwd_levels))
@@ -306,6 +350,30 @@ class CoopPlan(object):
     # FMAs then need no negated operand
     NEG_FACTORS = __import__("os").environ.get("GLEIPNIR_NEG_FACTORS", "0") == "1"
 
+    # group the pivots of the elimination by levels of its DAG (shared-memory broadcast only).  Measured on the JARM
+    # network (15 levels instead of 32 pivots; tools/jarm_check.py, ODE steps/s): off 9.48e7, whole levels 8.45e7 (a
+    # level of ten pivots keeps 25 register pairs of row values alive), at most 2 pivots per group 9.37e7, 3: 9.2e7
+    # -- the elimination's store/sync/load round trips are not what a step waits for; left off.
+    LU_LEVELS = __import__("os").environ.get("GLEIPNIR_LU_LEVELS", "0") == "1"
+    LU_LEVEL_WIDTH = int(__import__("os").environ.get("GLEIPNIR_LU_LEVEL_WIDTH", "0"))
+
+    def lu_levels(self):
+        """Pivots grouped so that no two of a level couple: level(c) = 1 + max level of the earlier pivots c' with
+        L[c][c'] != 0 or U[c'][c] != 0 (filled pattern)."""
+        Q, nc = self.filled, self.nc
+        lev = [0] * nc
+        for c in range(nc):
+            deps = [lev[q] for q in range(c) if Q[c, q] or Q[q, c]]
+            lev[c] = 1 + max(deps) if deps else 0
+        levels = [[c for c in range(nc) if lev[c] == l] for l in range(max(lev) + 1 if nc else 0)]
+        w = self.LU_LEVEL_WIDTH                             # wide levels are cut: every pivot keeps its row in registers
+        return [lv[i:i + w] for lv in levels for i in range(0, len(lv), w)] if w > 0 else levels
+
+    def lu_level_stride(self):
+        """Doubles per broadcast buffer of a level (pivot + row of every pivot of the level, each padded to a pair)."""
+        ops = dict(self.lu_ops)
+        return max([sum(len(ops[c]) + 1 + ((len(ops[c]) + 1) & 1) for c in level) for level in self.lu_levels()] + [2])
+
     def lu_buf_stride(self):
         """Doubles per broadcast buffer of the elimination (pivot + longest pivot row, padded to a pair)."""
         m = max([len(cols) + 1 for _, cols in self.lu_ops] + [2])
@@ -313,7 +381,8 @@ class CoopPlan(object):
 
     def xs_stride(self):
         """Doubles per broadcast buffer of the substitution: one slot per lane plus one per leaf."""
-        return max(max(self.gl, self.nc) + max(self.nx, 0), self.lu_buf_stride())
+        return max(max(self.gl, self.nc) + max(self.nx, 0), self.lu_buf_stride(),
+                   self.lu_level_stride() if self.LU_LEVELS else 0)
 
     def cuda_scale_u(self):
         """After the factorisation: U -> D^-1 U (unit upper triangular), so that the backward substitution needs
